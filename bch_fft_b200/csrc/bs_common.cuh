@@ -1,0 +1,125 @@
+// Bitsliced GF(2^m) primitives shared by every kernel.
+//
+// Representation ("slab"): 32 independent items (polynomials or codewords) are processed
+// together.  One field element per item is held as M 32-bit plane words; bit l of plane b is
+// bit b (coefficient of x^b, polynomial basis of libbase/finite_field.c:19-48 in the
+// reference) of item l's element.  Field addition is a plane-wise XOR, multiplication is
+// AND/XOR logic only (LOP3 on sm_100a): no log/exp tables, no bank conflicts, no branches.
+#pragma once
+#include <stdint.h>
+
+#ifdef BCHFFT_EMU
+// tools/cudaemu/cudaemu.h is force-included by the emulator build
+#else
+#include <cuda_runtime.h>
+#define BCHFFT_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define BCHFFT_DYN_SMEM(type, name) \
+  extern __shared__ __align__(16) unsigned char bchfft_dyn_smem_raw[]; \
+  type *name = reinterpret_cast<type *>(bchfft_dyn_smem_raw)
+#endif
+
+namespace bchfft {
+
+// Reduction polynomials of the reference's field table (libbase/finite_field.c:9-18,32-35),
+// x^m term included; index = m.  m >= 26 are not primitive there and are not supported here.
+__host__ __device__ constexpr uint32_t field_poly(int m)
+{
+  constexpr uint32_t t[26] = {0,        0,        0x7,      0xB,      0x13,     0x25,    0x43,
+                              0x83,     0x171,    0x211,    0x409,    0x805,    0x1099,  0x201B,
+                              0x5803,   0x8003,   0x1002D,  0x20009,  0x40081,  0x80063, 0x100009,
+                              0x200005, 0x400003, 0x800021, 0x100001B, 0x2000009};
+  return (m >= 2 && m <= 25) ? t[m] : 0;
+}
+
+// plane words per element in HBM slabs: M rounded up to a multiple of 4 so that one element is
+// a whole number of 16-byte vectors
+__host__ __device__ constexpr int plane_stride(int m) { return (m + 3) & ~3; }
+
+// p[0 .. 2M-2] -> p[0 .. M-1] modulo the field polynomial (top-down so that every fold-in lands
+// on a plane that is reduced later or is final)
+template <int M>
+__device__ __forceinline__ void bs_reduce(uint32_t (&p)[2 * M - 1])
+{
+  constexpr uint32_t taps = field_poly(M) & ((1u << M) - 1u);
+#pragma unroll
+  for (int k = 2 * M - 2; k >= M; --k) {
+#pragma unroll
+    for (int e = 0; e < M; ++e)
+      if ((taps >> e) & 1u) p[k - M + e] ^= p[k];
+  }
+}
+
+// a <- a * c, c one field element shared by the 32 items of the slab (every additive-FFT
+// multiplier is such a data-independent constant): M*M AND-XOR (one LOP3 each) + reduction.
+template <int M>
+__device__ __forceinline__ void bs_mul_scalar(uint32_t (&a)[M], uint32_t c)
+{
+  uint32_t p[2 * M - 1];
+#pragma unroll
+  for (int k = 0; k < 2 * M - 1; ++k) p[k] = 0u;
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const uint32_t mask = 0u - ((c >> j) & 1u);
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i + j] ^= a[i] & mask;
+  }
+  bs_reduce<M>(p);
+#pragma unroll
+  for (int i = 0; i < M; ++i) a[i] = p[i];
+}
+
+// acc <- acc + a * c
+template <int M>
+__device__ __forceinline__ void bs_mad_scalar(uint32_t (&acc)[M], const uint32_t (&a)[M], uint32_t c)
+{
+  uint32_t p[2 * M - 1];
+#pragma unroll
+  for (int k = 0; k < 2 * M - 1; ++k) p[k] = (k < M) ? acc[k] : 0u;
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const uint32_t mask = 0u - ((c >> j) & 1u);
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i + j] ^= a[i] & mask;
+  }
+  bs_reduce<M>(p);
+#pragma unroll
+  for (int i = 0; i < M; ++i) acc[i] = p[i];
+}
+
+// In-place transpose of a 32x32 bit matrix held as 32 words, LSB-first: afterwards bit j of
+// x[i] is the old bit i of x[j].  Converts 32 per-item values <-> 32 plane words.
+__device__ __forceinline__ void transpose32(uint32_t (&x)[32])
+{
+#pragma unroll
+  for (int s = 4; s >= 0; --s) {
+    const int j = 1 << s;
+    const uint32_t m = (s == 4) ? 0x0000FFFFu : (s == 3) ? 0x00FF00FFu : (s == 2) ? 0x0F0F0F0Fu
+                     : (s == 1) ? 0x33333333u : 0x55555555u;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k & j) continue;
+      const uint32_t t = ((x[k] >> j) ^ x[k + j]) & m;
+      x[k + j] ^= t;
+      x[k] ^= t << j;
+    }
+  }
+}
+
+// scalar (per-thread, table-free) GF(2^m) multiply used where an operand is data, e.g. the
+// Berlekamp-Massey recurrence: shift-and-add with interleaved reduction.
+template <int M>
+__host__ __device__ __forceinline__ uint32_t gf_mul(uint32_t a, uint32_t b)
+{
+  constexpr uint32_t poly = field_poly(M);
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = M - 1; i >= 0; --i) {
+    r <<= 1;
+    if (r & (1u << M)) r ^= poly;
+    if ((b >> i) & 1u) r ^= a;
+  }
+  return r;
+}
+
+}  // namespace bchfft

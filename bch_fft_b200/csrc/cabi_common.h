@@ -1,0 +1,66 @@
+// Internal declarations shared by the translation units behind include/bchfft_cuda.h.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "bs_common.cuh"
+#include "gm_plan.h"
+#include "fft_kernels.cuh"
+#include "../../include/bchfft_cuda.h"
+
+namespace bchfft {
+
+void set_error(const char *fmt, ...);
+extern uint64_t g_launches;
+
+#define BCHFFT_CUDA_TRY(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      bchfft::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__,  \
+                        __LINE__);                                                         \
+      return BCHFFT_ERR_CUDA;                                                              \
+    }                                                                                      \
+  } while (0)
+
+#define BCHFFT_CHECK_LAUNCH()                                                              \
+  do {                                                                                     \
+    bchfft::g_launches++;                                                                  \
+    BCHFFT_CUDA_TRY(cudaGetLastError());                                                   \
+  } while (0)
+
+// field degrees the kernels are instantiated for
+#ifndef BCHFFT_M_LIST
+#define BCHFFT_M_LIST(X) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20)
+#endif
+
+struct DeviceBuffer {
+  void *p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need);  // grow-only
+  void release();
+};
+
+}  // namespace bchfft
+
+struct bchfft_field {
+  int device = 0;
+  uint32_t m = 0, n = 0, order = 0;
+  int ps = 0;      // plane words per element in HBM
+  int t_max = 0;   // log2(tile positions) that fits shared memory
+  cudaStream_t stream = nullptr;
+  std::vector<uint32_t> h_exp, h_log;
+  uint32_t *d_tw = nullptr, *d_gam = nullptr, *d_perm_exp = nullptr, *d_perm_nat = nullptr;
+  uint32_t *d_exp = nullptr, *d_log = nullptr;
+  bchfft::FftTables tab;
+  std::map<int, bchfft::GmPlan> plans;   // keyed by K
+  bchfft::DeviceBuffer ws;               // slab workspace
+  bchfft::DeviceBuffer stage_in, stage_out, stage_aux;  // device staging for the _host variants
+  size_t chunk_bytes = 0;                // workspace budget per chunk of slabs
+  bool fft_attr_set = false;
+  // multiplicative FFT state (lazily built)
+  void *mfft = nullptr;
+};

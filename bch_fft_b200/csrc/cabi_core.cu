@@ -1,0 +1,220 @@
+// C-ABI plumbing: error text, device helpers, field contexts (see include/bchfft_cuda.h).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "cabi_common.h"
+
+namespace bchfft {
+
+static thread_local char g_err[512] = "";
+uint64_t g_launches = 0;
+
+void set_error(const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int DeviceBuffer::reserve(size_t need)
+{
+  if (need <= bytes) return BCHFFT_OK;
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+  BCHFFT_CUDA_TRY(cudaMalloc(&p, need));
+  bytes = need;
+  return BCHFFT_OK;
+}
+
+void DeviceBuffer::release()
+{
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+
+template <class T>
+static int upload_vec(const std::vector<T> &v, T **out)
+{
+  *out = nullptr;
+  BCHFFT_CUDA_TRY(cudaMalloc((void **)out, v.size() * sizeof(T) + 16));
+  BCHFFT_CUDA_TRY(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return BCHFFT_OK;
+}
+
+}  // namespace bchfft
+
+using namespace bchfft;
+
+extern "C" const char *bchfft_last_error(void) { return g_err; }
+
+extern "C" int bchfft_is_emulated(void)
+{
+#ifdef BCHFFT_EMU
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+extern "C" int bchfft_device_count(void)
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    return BCHFFT_ERR_CUDA;
+  }
+  return n;
+}
+
+extern "C" uint64_t bchfft_launch_count(void) { return g_launches; }
+extern "C" void bchfft_launch_count_reset(void) { g_launches = 0; }
+
+extern "C" int bchfft_dev_alloc(int device, size_t bytes, void **out)
+{
+  BCHFFT_CUDA_TRY(cudaSetDevice(device));
+  BCHFFT_CUDA_TRY(cudaMalloc(out, bytes ? bytes : 1));
+  return BCHFFT_OK;
+}
+
+extern "C" int bchfft_dev_free(int device, void *p)
+{
+  BCHFFT_CUDA_TRY(cudaSetDevice(device));
+  BCHFFT_CUDA_TRY(cudaFree(p));
+  return BCHFFT_OK;
+}
+
+extern "C" int bchfft_dev_upload(int device, void *d_dst, const void *h_src, size_t bytes)
+{
+  BCHFFT_CUDA_TRY(cudaSetDevice(device));
+  BCHFFT_CUDA_TRY(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+  return BCHFFT_OK;
+}
+
+extern "C" int bchfft_dev_download(int device, void *h_dst, const void *d_src, size_t bytes)
+{
+  BCHFFT_CUDA_TRY(cudaSetDevice(device));
+  BCHFFT_CUDA_TRY(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+  return BCHFFT_OK;
+}
+
+static bool m_supported(uint32_t m)
+{
+#define X(M) if (m == M) return true;
+  BCHFFT_M_LIST(X)
+#undef X
+  return false;
+}
+
+extern "C" int bchfft_field_create(int device, uint32_t m, const uint32_t *exp, const uint32_t *log,
+                                   bchfft_field **out)
+{
+  if (!out || !exp || !log) {
+    set_error("bchfft_field_create: null argument");
+    return BCHFFT_ERR_ARG;
+  }
+  *out = nullptr;
+  if (!m_supported(m)) {
+    set_error("bchfft_field_create: GF(2^%u) is not among the compiled field degrees", m);
+    return BCHFFT_ERR_UNSUPPORTED;
+  }
+  int ndev = bchfft_device_count();
+  if (ndev <= 0) {
+    if (ndev == 0) set_error("bchfft_field_create: no CUDA device (there is no CPU fallback)");
+    return BCHFFT_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error("bchfft_field_create: device %d out of range (%d visible)", device, ndev);
+    return BCHFFT_ERR_ARG;
+  }
+  const uint32_t n = 1u << m;
+  // sanity-check the caller's tables against the reference convention (finite_field.c:36-48)
+  if (exp[0] != 1u || exp[1] != 2u || log[0] != n - 1u || log[1] != 0u || exp[n - 1] != 0u ||
+      ((exp[m] ^ n) != field_poly((int)m))) {
+    set_error("bchfft_field_create: exp/log tables do not describe GF(2^%u) with the reference's "
+              "reduction polynomial 0x%x", m, field_poly((int)m));
+    return BCHFFT_ERR_ARG;
+  }
+  BCHFFT_CUDA_TRY(cudaSetDevice(device));
+  bchfft_field *f = new bchfft_field();
+  f->device = device;
+  f->m = m;
+  f->n = n;
+  f->order = n - 1u;
+  f->ps = plane_stride((int)m);
+  {
+    // largest power-of-two tile whose M planes fit the 227 KB a CTA may use on sm_100a
+    int t = 0;
+    while ((size_t)(4u * m) << (t + 1) <= (size_t)227 * 1024) t++;
+    f->t_max = t;
+    // test hook: smaller tiles force the multi-pass schedule on small fields
+    const char *tenv = getenv("BCHFFT_TMAX");
+    if (tenv && atoi(tenv) >= 2 && atoi(tenv) < t) f->t_max = atoi(tenv);
+  }
+  f->h_exp.assign(exp, exp + n);
+  f->h_log.assign(log, log + n);
+  const char *env = getenv("BCHFFT_CHUNK_MB");
+  f->chunk_bytes = (size_t)(env ? atoi(env) : 64) << 20;
+
+  GmConstants c = gm_constants((int)m, exp, log);
+  std::vector<uint32_t> perm_exp(n), perm_nat(n);
+  for (uint32_t k = 0; k < n; k++) perm_nat[k] = bitrev_bits(k, (int)m);
+  for (uint32_t i = 0; i < n - 1u; i++) perm_exp[i] = perm_nat[exp[i]];
+  perm_exp[n - 1] = 0;
+  int rc = BCHFFT_OK;
+  if ((rc = upload_vec(c.tw, &f->d_tw)) || (rc = upload_vec(c.gam, &f->d_gam)) ||
+      (rc = upload_vec(perm_exp, &f->d_perm_exp)) || (rc = upload_vec(perm_nat, &f->d_perm_nat)) ||
+      (rc = upload_vec(f->h_exp, &f->d_exp)) || (rc = upload_vec(f->h_log, &f->d_log))) {
+    bchfft_field_destroy(f);
+    return rc;
+  }
+  memset(&f->tab, 0, sizeof f->tab);
+  f->tab.tw = f->d_tw;
+  f->tab.gam = f->d_gam;
+  for (uint32_t d = 0; d < m; d++) {
+    f->tab.tw_off[d] = c.tw_off[d];
+    f->tab.gam_off[d] = c.gam_off[d];
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    bchfft_field_destroy(f);
+    return BCHFFT_ERR_CUDA;
+  }
+  *out = f;
+  return BCHFFT_OK;
+}
+
+extern "C" void bchfft_mfft_release(bchfft_field *f);
+
+extern "C" void bchfft_field_destroy(bchfft_field *f)
+{
+  if (!f) return;
+  cudaSetDevice(f->device);
+  if (f->stream) cudaStreamSynchronize(f->stream);
+  bchfft_mfft_release(f);
+  cudaFree(f->d_tw);
+  cudaFree(f->d_gam);
+  cudaFree(f->d_perm_exp);
+  cudaFree(f->d_perm_nat);
+  cudaFree(f->d_exp);
+  cudaFree(f->d_log);
+  f->ws.release();
+  f->stage_in.release();
+  f->stage_out.release();
+  f->stage_aux.release();
+  if (f->stream) cudaStreamDestroy(f->stream);
+  delete f;
+}
+
+extern "C" int bchfft_field_sync(bchfft_field *f)
+{
+  if (!f) return BCHFFT_ERR_ARG;
+  BCHFFT_CUDA_TRY(cudaSetDevice(f->device));
+  BCHFFT_CUDA_TRY(cudaStreamSynchronize(f->stream));
+  return BCHFFT_OK;
+}

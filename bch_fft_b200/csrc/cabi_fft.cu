@@ -1,0 +1,167 @@
+// Batched additive FFT driver (see include/bchfft_cuda.h, bchfft_additive_fft_*).
+#include "cabi_common.h"
+
+namespace bchfft {
+
+static int ceil_log2(uint32_t x)
+{
+  int k = 0;
+  while ((1ull << k) < x) k++;
+  return k;
+}
+
+template <int M>
+static int fft_run(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride, uint32_t *d_results,
+                   size_t result_stride, uint32_t *d_natural, size_t natural_stride,
+                   uint32_t num_terms, size_t batch, cudaStream_t stream)
+{
+  constexpr int PS = plane_stride(M);
+  const uint32_t n = f->n;
+  // coefficients 0..num_terms take part (additive_fft.c:99); K = log2 of the padded count
+  const uint32_t ncoef = (num_terms >= n - 1u ? n - 1u : num_terms) + 1u;
+  const int K = ceil_log2(ncoef);
+  auto it = f->plans.find(K);
+  if (it == f->plans.end()) it = f->plans.emplace(K, gm_plan(M, K, f->t_max)).first;
+  const GmPlan &plan = it->second;
+
+  const size_t fwd_words = ((size_t)1 << K) * PS;            // per slab
+  const size_t bwd_words = (size_t)n * PS;
+  const bool separate = K < M;                                // broadcast needs a second buffer
+  const size_t slab_bytes = (fwd_words + (separate ? bwd_words : 0)) * sizeof(uint32_t);
+  const size_t nslabs = (batch + 31) / 32;
+  size_t chunk = f->chunk_bytes / slab_bytes;
+  if (chunk < 1) chunk = 1;
+  if (chunk > nslabs) chunk = nslabs;
+  if (chunk > 65535) chunk = 65535;                           // gridDim.y limit
+  int rc = f->ws.reserve(chunk * slab_bytes);
+  if (rc) return rc;
+  uint32_t *bufF = (uint32_t *)f->ws.p;
+  uint32_t *bufB = separate ? bufF + chunk * fwd_words : bufF;
+
+  if (!f->fft_attr_set) {   // per context: the opt-in is a per-device function attribute
+    BCHFFT_CUDA_TRY(cudaFuncSetAttribute(k_gm_pass<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(((size_t)4 * M) << f->t_max)));
+    f->fft_attr_set = true;
+  }
+  const int nt_io = 128;
+#ifdef BCHFFT_EMU
+  const int nt_pass = 32;
+#else
+  const int nt_pass = 512;
+#endif
+  for (size_t s0 = 0; s0 < nslabs; s0 += chunk) {
+    const size_t cs = (nslabs - s0 < chunk) ? nslabs - s0 : chunk;
+    const uint32_t items = (uint32_t)((batch - s0 * 32 < cs * 32) ? batch - s0 * 32 : cs * 32);
+    const uint32_t *src = d_polys + s0 * 32 * poly_stride;
+    {
+      dim3 grid((unsigned)((((size_t)1 << K) + nt_io - 1) / nt_io), (unsigned)cs);
+      BCHFFT_LAUNCH(k_bitslice_in<M>, grid, dim3(nt_io), 0, stream, src, poly_stride, items, ncoef,
+                    (uint32_t)K, bufF);
+      BCHFFT_CHECK_LAUNCH();
+    }
+    for (size_t pi = 0; pi < plan.passes.size(); pi++) {
+      const PassDesc &pd = plan.passes[pi];
+      const bool bw = pd.backward != 0;
+      const bool first_bw = bw && (int)pi == plan.first_backward;
+      const uint32_t *psrc = (bw && !first_bw) ? bufB : bufF;
+      uint32_t *pdst = bw ? bufB : bufF;
+      const size_t src_words = (bw && !first_bw) ? bwd_words : fwd_words;
+      const size_t dst_words = bw ? bwd_words : fwd_words;
+      dim3 grid(1u << (pd.dom_bits - pd.t), (unsigned)cs);
+      const size_t smem = ((size_t)4 * M) << pd.t;
+      BCHFFT_LAUNCH(k_gm_pass<M>, grid, dim3(nt_pass), smem, stream, psrc, pdst, src_words,
+                    dst_words, f->tab, pd);
+      BCHFFT_CHECK_LAUNCH();
+    }
+    if (d_results) {
+      dim3 grid((n - 1u + nt_io - 1) / nt_io, (unsigned)cs);
+      BCHFFT_LAUNCH(k_gather_out<M>, grid, dim3(nt_io), 0, stream, (const uint32_t *)bufB, bwd_words,
+                    (const uint32_t *)f->d_perm_exp, n - 1u, d_results + s0 * 32 * result_stride,
+                    result_stride, items);
+      BCHFFT_CHECK_LAUNCH();
+    }
+    if (d_natural) {
+      dim3 grid((n + nt_io - 1) / nt_io, (unsigned)cs);
+      BCHFFT_LAUNCH(k_gather_out<M>, grid, dim3(nt_io), 0, stream, (const uint32_t *)bufB, bwd_words,
+                    (const uint32_t *)f->d_perm_nat, n, d_natural + s0 * 32 * natural_stride,
+                    natural_stride, items);
+      BCHFFT_CHECK_LAUNCH();
+    }
+  }
+  return BCHFFT_OK;
+}
+
+}  // namespace bchfft
+
+using namespace bchfft;
+
+extern "C" int bchfft_additive_fft_dev(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride,
+                                       uint32_t *d_results, size_t result_stride, uint32_t *d_natural,
+                                       size_t natural_stride, uint32_t num_terms, size_t batch,
+                                       void *stream)
+{
+  if (!f || !d_polys || (!d_results && !d_natural)) {
+    set_error("bchfft_additive_fft_dev: null argument");
+    return BCHFFT_ERR_ARG;
+  }
+  if (poly_stride < f->n || (d_results && result_stride < f->n - 1u) ||
+      (d_natural && natural_stride < f->n)) {
+    set_error("bchfft_additive_fft_dev: stride smaller than the field size");
+    return BCHFFT_ERR_ARG;
+  }
+  if (batch == 0) return BCHFFT_OK;
+  BCHFFT_CUDA_TRY(cudaSetDevice(f->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : f->stream;
+  switch (f->m) {
+#define X(M)                                                                                      \
+  case M:                                                                                         \
+    return fft_run<M>(f, d_polys, poly_stride, d_results, result_stride, d_natural, natural_stride, \
+                      num_terms, batch, st);
+    BCHFFT_M_LIST(X)
+#undef X
+  }
+  set_error("bchfft_additive_fft_dev: unsupported field degree %u", f->m);
+  return BCHFFT_ERR_UNSUPPORTED;
+}
+
+extern "C" int bchfft_additive_fft_host(bchfft_field *f, const uint32_t *polys, size_t poly_stride,
+                                        uint32_t *results, size_t result_stride, uint32_t *natural,
+                                        size_t natural_stride, uint32_t num_terms, size_t batch)
+{
+  if (!f || !polys || (!results && !natural)) {
+    set_error("bchfft_additive_fft_host: null argument");
+    return BCHFFT_ERR_ARG;
+  }
+  if (batch == 0) return BCHFFT_OK;
+  BCHFFT_CUDA_TRY(cudaSetDevice(f->device));
+  const uint32_t n = f->n;
+  // stage in chunks so that device staging stays bounded (256 MiB of input per chunk)
+  size_t per = ((size_t)256 << 20) / (poly_stride * sizeof(uint32_t));
+  per = per < 32 ? 32 : (per / 32) * 32;
+  if (per > batch) per = batch;
+  int rc;
+  if ((rc = f->stage_in.reserve(per * (size_t)n * 4))) return rc;
+  if (results && (rc = f->stage_out.reserve(per * (size_t)n * 4))) return rc;
+  if (natural && (rc = f->stage_aux.reserve(per * (size_t)n * 4))) return rc;
+  for (size_t i0 = 0; i0 < batch; i0 += per) {
+    const size_t cnt = batch - i0 < per ? batch - i0 : per;
+    uint32_t *d_in = (uint32_t *)f->stage_in.p;
+    BCHFFT_CUDA_TRY(cudaMemcpy2DAsync(d_in, (size_t)n * 4, polys + i0 * poly_stride, poly_stride * 4,
+                                      (size_t)n * 4, cnt, cudaMemcpyHostToDevice, f->stream));
+    uint32_t *d_res = results ? (uint32_t *)f->stage_out.p : nullptr;
+    uint32_t *d_nat = natural ? (uint32_t *)f->stage_aux.p : nullptr;
+    rc = bchfft_additive_fft_dev(f, d_in, n, d_res, n, d_nat, n, num_terms, cnt, f->stream);
+    if (rc) return rc;
+    // the reference never writes entry n-1 of po_result (additive_fft.c:20): copy n-1 per row
+    if (results)
+      BCHFFT_CUDA_TRY(cudaMemcpy2DAsync(results + i0 * result_stride, result_stride * 4, d_res,
+                                        (size_t)n * 4, (size_t)(n - 1) * 4, cnt,
+                                        cudaMemcpyDeviceToHost, f->stream));
+    if (natural)
+      BCHFFT_CUDA_TRY(cudaMemcpy2DAsync(natural + i0 * natural_stride, natural_stride * 4, d_nat,
+                                        (size_t)n * 4, (size_t)n * 4, cnt, cudaMemcpyDeviceToHost,
+                                        f->stream));
+    BCHFFT_CUDA_TRY(cudaStreamSynchronize(f->stream));
+  }
+  return BCHFFT_OK;
+}

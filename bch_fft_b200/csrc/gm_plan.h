@@ -1,0 +1,218 @@
+// Host-side planning for the batched additive FFT: Gao-Mateer constants and the schedule of
+// tile passes.  Pure C++ (no CUDA), so it is unit-testable on the CPU.
+//
+// The transform evaluated is the one of the reference's libfft/additive_fft.c:23-178
+// (von zur Gathen-Gerhard, evaluation points = all field elements, natural order with basis
+// 1, 2, 4, ...).  All arithmetic is exact, so any correct algorithm is bit-identical; we use
+// the Gao-Mateer recursion (Taylor expansion at x^2+x) because every multiplier is a
+// data-independent constant.  In-place iterative form (validated in tools/gm_model.py):
+//
+//   forward, depth d = 0..K-1 (domain: positions < 2^K, K = ceil(log2(#coefficients))):
+//       TW(d)     a[p] *= tw[d][p >> d]
+//       TY(d,lo)  lo = K-2 .. d:  on position bits (lo+1, lo):  Q2 ^= Q3 ; Q1 ^= Q2
+//   broadcast the 2^K values over the 2^(m-K) cosets (positions p + c*2^K)
+//   backward, depth d = K-1..0 (domain: all 2^m positions):
+//       BF(d)     lo' = lo + gam[d][p >> (d+1)] * hi ; hi' = lo' + hi     (pair = bit d of p)
+//   result: position p holds P(bitrev_m(p)).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+namespace bchfft {
+
+enum : uint8_t { OP_TW = 0, OP_TY = 1, OP_BF = 2 };
+
+struct PassOp {
+  uint8_t type, d, lo, pad;
+};
+
+constexpr int kMaxOps = 120;
+
+// One pass = one kernel launch; every CTA loads a tile of 2^t positions (window = up to two
+// contiguous ranges of position bits), runs `nops` ops on it in shared memory, stores it.
+struct PassDesc {
+  uint32_t nops;
+  uint32_t t;              // tile bits = n0 + n1
+  uint32_t dom_bits;       // positions in the pass domain = 2^dom_bits
+  uint32_t a0, n0, a1, n1; // window ranges [a0, a0+n0) and [a1, a1+n1); local bit i<n0 -> a0+i
+  uint32_t src_mask;       // source position = p & src_mask (broadcast load when < 2^dom_bits-1)
+  uint32_t backward;       // 0: forward-domain pass, 1: backward-domain pass
+  PassOp ops[kMaxOps];
+};
+
+struct GmConstants {
+  int m = 0;
+  std::vector<uint32_t> tw;       // concatenated tw[d][0 .. 2^(m-d))
+  std::vector<uint32_t> gam;      // concatenated gam[d][0 .. 2^(m-d-1))
+  std::vector<uint32_t> tw_off;   // m entries
+  std::vector<uint32_t> gam_off;  // m entries
+};
+
+inline uint32_t bitrev_bits(uint32_t x, int bits)
+{
+  uint32_t r = 0;
+  for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+  return r;
+}
+
+// exp/log: the caller's TfiniteField tables (libbase/finite_field.c:19-48 layout:
+// exp[i] = x^i, log[0] = order).
+inline GmConstants gm_constants(int m, const uint32_t *exp, const uint32_t *log)
+{
+  const uint32_t order = (1u << m) - 1u;
+  auto mul = [&](uint32_t a, uint32_t b) -> uint32_t {
+    if (!a || !b) return 0;
+    uint32_t s = log[a] + log[b];
+    if (s >= order) s -= order;
+    return exp[s];
+  };
+  GmConstants c;
+  c.m = m;
+  std::vector<uint32_t> basis(m);
+  for (int i = 0; i < m; i++) basis[i] = 1u << i;
+  for (int d = 0; d < m; d++) {
+    const int k = m - d;
+    const uint32_t tau = basis[k - 1];
+    c.tw_off.push_back((uint32_t)c.tw.size());
+    uint32_t pw = 1;
+    for (uint32_t i = 0; i < (1u << k); i++) {
+      c.tw.push_back(pw);
+      pw = mul(pw, tau);
+    }
+    const uint32_t itau = exp[(order - log[tau]) % order];
+    std::vector<uint32_t> g(k - 1);
+    for (int i = 0; i < k - 1; i++) g[i] = mul(basis[i], itau);
+    c.gam_off.push_back((uint32_t)c.gam.size());
+    for (uint32_t q = 0; q < (1u << (k - 1)); q++) {
+      const uint32_t j = bitrev_bits(q, k - 1);
+      uint32_t v = 0;
+      for (int b = 0; b < k - 1; b++)
+        if ((j >> b) & 1u) v ^= g[b];
+      c.gam.push_back(v);
+    }
+    std::vector<uint32_t> next(k - 1);
+    for (int i = 0; i < k - 1; i++) next[i] = mul(g[i], g[i]) ^ g[i];
+    basis = next;
+  }
+  return c;
+}
+
+// ---- pass planner -----------------------------------------------------------------------
+// number of maximal runs of set bits
+inline int bit_runs(uint32_t x)
+{
+  int r = 0;
+  while (x) {
+    x >>= __builtin_ctz(x);   // drop trailing zeros
+    r++;
+    while (x & 1u) x >>= 1;   // drop the run
+  }
+  return r;
+}
+
+// Grow `w` (a non-empty set of position bits within [0,dom), at most two runs) to
+// min(t, dom) bits keeping at most two runs.  Low bits are preferred so that the rows a tile
+// reads from HBM are contiguous: first extend the lowest run down to bit 0, then upward.
+inline uint32_t pad_window(uint32_t w, int t, int dom)
+{
+  const int want = t < dom ? t : dom;
+  while (__builtin_popcount(w) < want) {
+    const int lo0 = __builtin_ctz(w);
+    if (lo0 > 0) {
+      w |= 1u << (lo0 - 1);
+    } else {
+      int n0 = 0;
+      while ((w >> n0) & 1u) n0++;
+      w |= 1u << n0;           // free by construction; merges with the upper run when adjacent
+    }
+  }
+  return w;
+}
+
+inline void set_window(PassDesc &p, uint32_t w)
+{
+  // w has one or two runs
+  const int lo0 = __builtin_ctz(w);
+  int n0 = 0;
+  while ((w >> (lo0 + n0)) & 1u) n0++;
+  p.a0 = lo0;
+  p.n0 = n0;
+  const uint32_t rest = w & ~(((1u << n0) - 1u) << lo0);
+  if (rest) {
+    const int lo1 = __builtin_ctz(rest);
+    int n1 = 0;
+    while ((rest >> (lo1 + n1)) & 1u) n1++;
+    p.a1 = lo1;
+    p.n1 = n1;
+  } else {
+    p.a1 = lo0 + n0;
+    p.n1 = 0;
+  }
+  p.t = p.n0 + p.n1;
+}
+
+struct GmPlan {
+  int m, K, t;
+  std::vector<PassDesc> passes;  // forward passes first, then backward passes
+  int first_backward;
+};
+
+// t_max: largest tile (log2 positions) that fits the CTA's shared memory for this M.
+inline GmPlan gm_plan(int m, int K, int t_max)
+{
+  GmPlan plan;
+  plan.m = m;
+  plan.K = K;
+  plan.t = t_max;
+  struct Item { PassOp op; uint32_t bits; };
+  auto build = [&](const std::vector<Item> &stream, int dom, bool backward, uint32_t src_mask_first) {
+    size_t i = 0;
+    bool first = true;
+    const int t = t_max < dom ? t_max : dom;
+    do {
+      PassDesc p;
+      memset(&p, 0, sizeof p);
+      uint32_t w = 0;
+      while (i < stream.size() && p.nops < (uint32_t)kMaxOps) {
+        const uint32_t cand = w | stream[i].bits;
+        if (__builtin_popcount(cand) > t || bit_runs(cand) > 2) break;
+        w = cand;
+        p.ops[p.nops++] = stream[i].op;
+        i++;
+      }
+      if (dom > 0) {
+        if (w == 0) w = 1u;
+        w = pad_window(w, t, dom);
+        set_window(p, w);
+      } else {
+        p.a0 = p.n0 = p.a1 = p.n1 = p.t = 0;
+      }
+      p.dom_bits = dom;
+      p.backward = backward ? 1u : 0u;
+      p.src_mask = (first && backward) ? src_mask_first : 0xFFFFFFFFu;
+      first = false;
+      plan.passes.push_back(p);
+    } while (i < stream.size());
+  };
+  std::vector<Item> fwd, bwd;
+  for (int d = 0; d < K; d++) {
+    fwd.push_back({{OP_TW, (uint8_t)d, 0, 0}, 0u});
+    for (int lo = K - 2; lo >= d; lo--) fwd.push_back({{OP_TY, (uint8_t)d, (uint8_t)lo, 0}, 3u << lo});
+  }
+  for (int d = K - 1; d >= 0; d--) bwd.push_back({{OP_BF, (uint8_t)d, 0, 0}, 1u << d});
+  if (K == m && m <= t_max) {
+    // whole transform fits one tile: a single in-place pass does everything
+    std::vector<Item> all = fwd;
+    all.insert(all.end(), bwd.begin(), bwd.end());
+    plan.first_backward = 0;
+    build(all, m, true, 0xFFFFFFFFu);
+    return plan;
+  }
+  if (!fwd.empty()) build(fwd, K, false, 0xFFFFFFFFu);   // K = 0: constant polynomial, nothing to do
+  plan.first_backward = (int)plan.passes.size();
+  build(bwd, m, true, K < m ? ((1u << K) - 1u) : 0xFFFFFFFFu);
+  return plan;
+}
+
+}  // namespace bchfft
