@@ -1,0 +1,353 @@
+// Batched binary-BCH decode kernels (replace libbch/bch.c:228-562 of the reference run once per
+// codeword).  A slab is 32 codewords; bit l of a plane word belongs to codeword l of the slab.
+//
+//   k_syndrome     packed codewords -> bitsliced odd syndromes S_1, S_3, .. (bch.c:228-326)
+//   k_syn_finish   un-bitslice, S_2j = S_j^2, zero test
+//   k_bm           Berlekamp-Massey, one thread per codeword (bch.c:328-404)
+//   k_locate       error-locator evaluation at every field point through the truncated
+//                  additive FFT, root compaction (bch.c:406-490)
+//   k_correct      ok / corrected bookkeeping and the bit flips (bch.c:531-561)
+#pragma once
+#include "bs_common.cuh"
+#include "fft_kernels.cuh"
+
+namespace bchfft {
+
+constexpr int kSynSub = 256;  // positions per LFSR work item
+
+// ---- syndromes ------------------------------------------------------------------------------
+// S_j = c(x^j) = (c mod Q_j)(x^j) for any multiple Q_j of the minimal polynomial of x^j.  Every
+// work item (odd j, sub-chunk q) runs a bitsliced LFSR of degree M over kSynSub positions
+// (M LOP3 per position for 32 codewords), then folds its remainder r into the syndrome with
+// the constants x^(j (b + q kSynSub)), b < M: S_j += sum_b r_b x^(j(b + off)).
+//
+// grid = (position chunks, slabs); chunk = `chunk_pos` positions (multiple of kSynSub, <= the
+// shared-memory plane buffer); acc: [slab][nodd][M] plane words, zero-initialised, XOR-merged;
+// parity: [slab] plane word = XOR of all codeword bits (c(1), the reference's FFT-path
+// syndrome[0]).
+template <int M>
+__global__ void __launch_bounds__(512, 1)
+k_syndrome(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32_t length_bits,
+           uint32_t batch, uint32_t chunk_pos, uint32_t nodd, const uint32_t *__restrict__ taps,
+           const uint32_t *__restrict__ fold, uint32_t nsub_total, uint32_t *__restrict__ acc,
+           uint32_t *__restrict__ parity)
+{
+  BCHFFT_DYN_SMEM(uint32_t, smem);
+  const uint32_t slab = blockIdx.y;
+  const uint32_t pos0 = blockIdx.x * chunk_pos;
+  const uint32_t nsub = chunk_pos / kSynSub;
+  // planes[p + p / kSynSub]: one word of padding per sub-chunk keeps items of different
+  // sub-chunks on different banks
+  uint32_t *planes = smem;
+  uint32_t *sacc = smem + chunk_pos + nsub;  // [nodd][M]
+  __shared__ uint32_t s_par;
+  if (threadIdx.x == 0) s_par = 0u;
+  for (uint32_t i = threadIdx.x; i < nodd * M; i += blockDim.x) sacc[i] = 0u;
+  __syncthreads();
+
+  // phase A: transpose 32 codewords x 32 positions blocks into plane words
+  uint32_t par = 0u;
+  for (uint32_t g = threadIdx.x; g < chunk_pos / 32; g += blockDim.x) {
+    const uint32_t w = pos0 / 32 + g;
+    uint32_t x[32];
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const uint32_t item = slab * 32u + l;
+      x[l] = (item < batch && w < words32_per_cw) ? words32[(size_t)item * words32_per_cw + w] : 0u;
+    }
+    // bits at positions >= length do not belong to the codeword (bch.c:258-262, 278)
+    const uint32_t first = w * 32u;
+    if (first + 32u > length_bits) {
+      const uint32_t keep = first < length_bits ? length_bits - first : 0u;
+      const uint32_t mask = keep ? (0xFFFFFFFFu >> (32u - keep)) : 0u;
+#pragma unroll
+      for (int l = 0; l < 32; ++l) x[l] &= mask;
+    }
+    transpose32(x);
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const uint32_t p = g * 32u + b;
+      planes[p + p / kSynSub] = x[b];
+      par ^= x[b];
+    }
+  }
+  if (par) atomicXor(&s_par, par);
+  __syncthreads();
+
+  // phase B: LFSR per (odd j, sub-chunk)
+  for (uint32_t item = threadIdx.x; item < nodd * nsub; item += blockDim.x) {
+    const uint32_t q = item / nodd, ji = item - q * nodd;
+    const uint32_t tp = taps[ji];
+    uint32_t tm[M], s[M];
+#pragma unroll
+    for (int b = 0; b < M; ++b) {
+      tm[b] = 0u - ((tp >> b) & 1u);
+      s[b] = 0u;
+    }
+    const uint32_t *src = planes + q * (kSynSub + 1);
+    for (int p = kSynSub - 1; p >= 0; --p) {
+      const uint32_t in = src[p];
+      const uint32_t fb = s[M - 1];
+#pragma unroll
+      for (int b = M - 1; b >= 1; --b) s[b] = s[b - 1] ^ (fb & tm[b]);
+      s[0] = in ^ (fb & tm[0]);
+    }
+    // fold: out = sum_b s[b] * fold[ji][q_global][b]
+    const uint32_t qg = blockIdx.x * nsub + q;
+    const uint32_t *fc = fold + ((size_t)ji * nsub_total + qg) * M;
+    uint32_t out[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) out[k] = 0u;
+#pragma unroll
+    for (int b = 0; b < M; ++b) {
+      const uint32_t c = fc[b];
+#pragma unroll
+      for (int k = 0; k < M; ++k) out[k] ^= s[b] & (0u - ((c >> k) & 1u));
+    }
+#pragma unroll
+    for (int k = 0; k < M; ++k)
+      if (out[k]) atomicXor(&sacc[ji * M + k], out[k]);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < nodd * M; i += blockDim.x)
+    if (sacc[i]) atomicXor(&acc[(size_t)slab * nodd * M + i], sacc[i]);
+  if (threadIdx.x == 0 && s_par) atomicXor(&parity[slab], s_par);
+}
+
+// One thread per codeword: syndromes[cw][0..d-1] (u32), flag[cw] (bch.c:317-324).
+// syndrome[0] follows the reference's method rule: parity of the word when the reference would
+// take its FFT path (bch.c:240-254), else 0 (value for every valid codeword on its direct path;
+// it never changes the decode result).
+template <int M>
+__global__ void k_syn_finish(const uint32_t *__restrict__ acc, const uint32_t *__restrict__ parity,
+                             uint32_t nodd, uint32_t d, uint32_t batch, uint32_t fft_rule,
+                             uint32_t *__restrict__ syn, int32_t *__restrict__ flag)
+{
+  const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cw >= batch) return;
+  const uint32_t slab = cw >> 5, l = cw & 31u;
+  uint32_t *s = syn + (size_t)cw * d;
+  uint32_t any = 0u;
+  s[0] = fft_rule ? ((parity[slab] >> l) & 1u) : 0u;
+  any |= s[0];
+  for (uint32_t i = 1; i < d; ++i) {
+    uint32_t v;
+    if (i & 1u) {
+      const uint32_t *a = acc + ((size_t)slab * nodd + (i >> 1)) * M;
+      v = 0u;
+#pragma unroll
+      for (int b = 0; b < M; ++b) v |= ((a[b] >> l) & 1u) << b;
+    } else {
+      const uint32_t h = s[i >> 1];
+      v = gf_mul<M>(h, h);
+    }
+    s[i] = v;
+    any |= v;
+  }
+  flag[cw] = any ? 1 : 0;
+}
+
+// ---- Berlekamp-Massey -----------------------------------------------------------------------
+// One thread per codeword, faithful to bch.c:328-404 including the rotation of the three
+// coefficient buffers (so that C[deg C + 1 .. L], which the reference leaves stale, is
+// reproduced from zero-initialised buffers).  bm: [3][d+1][batch] scratch, zero on entry
+// (coefficient-major: threads of a warp touch consecutive words).  Outputs: L[cw] and
+// elp[cw][0..d] = the final C buffer.
+template <int M>
+__global__ void k_bm(const uint32_t *__restrict__ syn, const int32_t *__restrict__ flag, uint32_t d,
+                     uint32_t batch, const uint32_t *__restrict__ gexp, const uint32_t *__restrict__ glog,
+                     uint32_t *__restrict__ bm, uint32_t *__restrict__ elp, uint32_t *__restrict__ Lout)
+{
+  const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cw >= batch) return;
+  const uint32_t order = (1u << M) - 1u;
+  const size_t cs = batch;                 // stride between coefficients
+  const size_t bs = (size_t)(d + 1) * cs;  // stride between buffers
+  uint32_t *A = bm + cw, *B = A + bs, *C = B + bs;
+  const uint32_t *s = syn + (size_t)cw * d;
+  uint32_t L = 0;
+  if (flag[cw]) {
+    uint32_t degA = 0, degB = 0, degC = 0, gap = 1, inv_b_log = 0;
+    B[0] = 1u;
+    C[0] = 1u;
+    for (uint32_t i = 0; i + 1 < d; ++i) {
+      uint32_t disc = s[i + 1];
+      for (uint32_t j = 1; j <= degC; ++j) disc ^= gf_mul<M>(C[j * cs], s[i + 1 - j]);
+      if (!disc) {
+        gap++;
+        continue;
+      }
+      const uint32_t dlog = glog[disc];
+      uint32_t sl = dlog + inv_b_log;
+      if (sl >= order) sl -= order;
+      const uint32_t scale = gexp[sl];
+      const uint32_t hiB = degB + gap;
+      const uint32_t keep = gap < degC + 1 ? gap : degC + 1;
+      uint32_t j = 0;
+      for (; j < keep; ++j) A[j * cs] = C[j * cs];
+      for (; j < gap; ++j) A[j * cs] = 0u;
+      for (; j <= hiB; ++j) A[j * cs] = gf_mul<M>(B[(j - gap) * cs], scale);
+      for (; j <= degC; ++j) A[j * cs] = 0u;
+      if (degC != hiB) {
+        degA = degC > hiB ? degC : hiB;
+        for (j = gap; j <= degC; ++j) A[j * cs] ^= C[j * cs];
+      } else {
+        for (j = gap; j <= degC; ++j) {
+          const uint32_t v = A[j * cs] ^ C[j * cs];
+          A[j * cs] = v;
+          if (v) degA = j;
+        }
+      }
+      if (2u * L <= i) {
+        L = i + 1u - L;
+        degB = degC;
+        uint32_t *t = B; B = C; C = t;
+        inv_b_log = order - dlog;
+        gap = 1;
+      } else {
+        gap++;
+      }
+      { uint32_t *t = C; C = A; A = t; }
+      degC = degA;
+    }
+  } else {
+    C[0] = 1u;
+  }
+  Lout[cw] = L;
+  uint32_t *e = elp + (size_t)cw * (d + 1);
+  for (uint32_t j = 0; j <= d; ++j) e[j] = C[j * cs];
+}
+
+// ---- root search ----------------------------------------------------------------------------
+// Evaluates the error locator of every codeword of a slab at all 2^M field points with the
+// truncated additive FFT: forward phase on the 2^K coefficients (K = ceil(log2(t+1)), tiny,
+// recomputed by every tile), values broadcast over the cosets, K butterfly levels on the tile.
+// A zero at position p = bitrev_M(k), k = x^i != 0, is an error at bit `order - i`
+// (bch.c:479-488, including the bit-0 quirk: i = 0 reports position `order`).
+// grid = (tiles per slab, slabs); dynamic smem = M * (2^t + 2^K) words.
+template <int M>
+__global__ void __launch_bounds__(512, 1)
+k_locate(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin,
+         const int32_t *__restrict__ flag, uint32_t d, uint32_t tcap, uint32_t batch, FftTables tab,
+         PassDesc fwd, PassDesc bwd, const uint32_t *__restrict__ glog, uint32_t *__restrict__ count,
+         uint32_t *__restrict__ positions, uint32_t pos_stride)
+{
+  BCHFFT_DYN_SMEM(uint32_t, smem);
+  const uint32_t K = fwd.dom_bits, TK = 1u << K, T = 1u << bwd.t;
+  uint32_t *S = smem;           // [M][T]
+  uint32_t *F = smem + M * T;   // [M][TK]
+  const uint32_t slab = blockIdx.y;
+  __shared__ uint32_t s_active;
+  if (threadIdx.x == 0) s_active = 0u;
+  __syncthreads();
+  // bitslice the coefficients: coefficient index i of the 32 codewords -> M plane words.
+  // Coefficients above L are not part of the polynomial (bch.c:444-445, 466).
+  for (uint32_t i = threadIdx.x; i < TK; i += blockDim.x) {
+    uint32_t x[32];
+    uint32_t act = 0u;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const uint32_t cw = slab * 32u + l;
+      uint32_t v = 0u;
+      if (cw < batch && flag[cw]) {
+        const uint32_t L = Lin[cw];
+        if (L <= tcap) {
+          act |= 1u << l;
+          if (i <= L) v = elp[(size_t)cw * (d + 1) + i];
+        }
+      }
+      x[l] = v;
+    }
+    transpose32(x);
+#pragma unroll
+    for (int b = 0; b < M; ++b) F[b * TK + i] = x[b];
+    if (i == 0) s_active = act;
+  }
+  __syncthreads();
+  if (s_active == 0u) return;  // nothing to locate in this slab (uniform across the CTA)
+  {
+    TileGeom g0 = tile_geom(fwd, 0u);
+    tile_run_ops<M>(F, TK, g0, tab, fwd);
+  }
+  const TileGeom g = tile_geom(bwd, blockIdx.x);
+  for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
+    const uint32_t src = g.pos(l) & (TK - 1u);
+#pragma unroll
+    for (int b = 0; b < M; ++b) S[b * T + l] = F[b * TK + src];
+  }
+  __syncthreads();
+  tile_run_ops<M>(S, T, g, tab, bwd);
+  const uint32_t active = s_active;
+  const uint32_t order = (1u << M) - 1u;
+  for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
+    uint32_t nz = 0u;
+#pragma unroll
+    for (int b = 0; b < M; ++b) nz |= S[b * T + l];
+    uint32_t roots = ~nz & active;
+    if (!roots) continue;
+    const uint32_t k = __brev(g.pos(l)) >> (32 - M);
+    if (k == 0u) continue;  // P(0) = C[0] = 1 for every active codeword; x^i never reaches 0
+    const uint32_t where = order - glog[k];
+    while (roots) {
+      const uint32_t lane = (uint32_t)__ffs((int)roots) - 1u;
+      roots &= roots - 1u;
+      const uint32_t cw = slab * 32u + lane;
+      const uint32_t idx = atomicAdd(&count[cw], 1u);
+      if (idx < pos_stride) positions[(size_t)cw * pos_stride + idx] = where;
+    }
+  }
+}
+
+// ---- verdict + correction (bch.c:531-561) ---------------------------------------------------
+// ok = 1, corrected = 0 for a clean word; L > t -> ok = 0, corrected = 0; otherwise corrected =
+// #roots and the bits are flipped iff #roots == L.  Flips outside the packed array (only
+// possible for shortened codes, where the reference writes out of bounds) are skipped.
+__global__ void k_correct(uint64_t *__restrict__ words, uint32_t words_per_cw, uint32_t batch,
+                          const int32_t *__restrict__ flag, const uint32_t *__restrict__ Lin,
+                          uint32_t tcap, const uint32_t *__restrict__ count,
+                          const uint32_t *__restrict__ positions, uint32_t pos_stride,
+                          uint8_t *__restrict__ ok, uint32_t *__restrict__ corrected)
+{
+  const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cw >= batch) return;
+  uint32_t good = 1u, found = 0u;
+  if (flag[cw]) {
+    const uint32_t L = Lin[cw];
+    good = 0u;
+    if (L <= tcap) {
+      found = count[cw];
+      if (found == L) {
+        good = 1u;
+        uint64_t *w = words + (size_t)cw * words_per_cw;
+        for (uint32_t i = 0; i < found; ++i) {
+          const uint32_t p = positions[(size_t)cw * pos_stride + i];
+          if ((p >> 6) < words_per_cw) w[p >> 6] ^= 1ull << (p & 63u);
+        }
+      }
+    }
+  }
+  if (ok) ok[cw] = (uint8_t)good;
+  if (corrected) corrected[cw] = found;
+}
+
+// descending sort of each codeword's position list (bch.c:479-488 emits i ascending, i.e.
+// positions descending); only the stage-level locate entry point needs the order.
+__global__ void k_sort_positions(uint32_t *__restrict__ positions, uint32_t pos_stride,
+                                 const uint32_t *__restrict__ count, uint32_t batch)
+{
+  const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cw >= batch) return;
+  uint32_t *p = positions + (size_t)cw * pos_stride;
+  const uint32_t n = count[cw] < pos_stride ? count[cw] : pos_stride;
+  for (uint32_t i = 1; i < n; ++i) {
+    const uint32_t v = p[i];
+    uint32_t j = i;
+    while (j > 0 && p[j - 1] < v) {
+      p[j] = p[j - 1];
+      --j;
+    }
+    p[j] = v;
+  }
+}
+
+}  // namespace bchfft

@@ -1,0 +1,515 @@
+// Batched BCH decode driver (see include/bchfft_cuda.h, bchfft_code_* / bchfft_bch_*).
+#include <stdlib.h>
+#include <string.h>
+
+#include "cabi_common.h"
+#include "bch_kernels.cuh"
+
+struct bchfft_code {
+  bchfft_field *f = nullptr;
+  uint32_t d = 0, t = 0, length = 0, gen_degree = 0;
+  uint32_t wpc = 0;          // 64-bit words per codeword
+  uint32_t nodd = 0;         // odd syndromes computed directly: S_1, S_3, .., S_{2 nodd - 1}
+  uint32_t syn_fft_rule = 0; // reference would take its FFT syndrome path (bch.c:240-254)
+  uint32_t chunk_pos = 0, nchunks = 0, nsub_total = 0;
+  uint32_t *d_taps = nullptr, *d_fold = nullptr;
+  bchfft::DeviceBuffer scratch, stage_words, stage_ok, stage_corr, stage_a, stage_b, stage_c;
+  bool attr_set = false;
+};
+
+namespace bchfft {
+
+static int ceil_log2u(uint32_t x)
+{
+  int k = 0;
+  while ((1ull << k) < x) k++;
+  return k;
+}
+
+// forward / backward descriptors of the truncated FFT used for root search: forward on the
+// 2^K coefficients (window [0,K)), backward K butterfly levels on tiles [0,t)
+static void locate_descs(int m, int K, int t, PassDesc &fwd, PassDesc &bwd)
+{
+  memset(&fwd, 0, sizeof fwd);
+  memset(&bwd, 0, sizeof bwd);
+  fwd.dom_bits = K;
+  fwd.t = K;
+  fwd.a0 = 0;
+  fwd.n0 = K;
+  fwd.a1 = K;
+  fwd.n1 = 0;
+  fwd.src_mask = 0xFFFFFFFFu;
+  for (int d = 0; d < K; d++) {
+    fwd.ops[fwd.nops++] = PassOp{OP_TW, (uint8_t)d, 0, 0};
+    for (int lo = K - 2; lo >= d; lo--) fwd.ops[fwd.nops++] = PassOp{OP_TY, (uint8_t)d, (uint8_t)lo, 0};
+  }
+  bwd.dom_bits = m;
+  bwd.t = t;
+  bwd.a0 = 0;
+  bwd.n0 = t;
+  bwd.a1 = t;
+  bwd.n1 = 0;
+  bwd.backward = 1;
+  bwd.src_mask = (1u << K) - 1u;
+  for (int d = K - 1; d >= 0; d--) bwd.ops[bwd.nops++] = PassOp{OP_BF, (uint8_t)d, 0, 0};
+}
+
+struct Scratch {
+  uint32_t *acc, *parity, *syn, *bm, *elp, *L, *count, *positions;
+  int32_t *flag;
+  uint32_t pos_stride;
+  size_t bytes_per_cw;
+};
+
+static size_t scratch_per_cw(const bchfft_code *c, uint32_t pos_stride, int M)
+{
+  const size_t d = c->d;
+  // acc+parity are per slab: ceil to one slab per 32 codewords
+  return sizeof(uint32_t) * (d + 3 * (d + 1) + (d + 1) + 3 + pos_stride) +
+         (sizeof(uint32_t) * ((size_t)c->nodd * M + 1) + 31) / 32 + 8;
+}
+
+static void carve(const bchfft_code *c, void *base, size_t cnt, uint32_t pos_stride, int M, Scratch &s)
+{
+  const size_t ns = (cnt + 31) / 32, d = c->d;
+  uint32_t *p = (uint32_t *)base;
+  s.acc = p;        p += ns * c->nodd * M;
+  s.parity = p;     p += ns;
+  s.count = p;      p += cnt;
+  s.bm = p;         p += 3 * (d + 1) * cnt;   // acc..bm are zeroed with one memset
+  s.syn = p;        p += cnt * d;
+  s.elp = p;        p += cnt * (d + 1);
+  s.L = p;          p += cnt;
+  s.flag = (int32_t *)p; p += cnt;
+  s.positions = p;  p += cnt * pos_stride;
+  s.pos_stride = pos_stride;
+}
+
+static size_t scratch_bytes(const bchfft_code *c, size_t cnt, uint32_t pos_stride, int M)
+{
+  const size_t ns = (cnt + 31) / 32, d = c->d;
+  return sizeof(uint32_t) * (ns * c->nodd * M + ns + cnt + 3 * (d + 1) * cnt + cnt * d +
+                             cnt * (d + 1) + cnt + cnt + cnt * pos_stride) + 64;
+}
+
+static size_t zero_bytes(const bchfft_code *c, size_t cnt, int M)
+{
+  const size_t ns = (cnt + 31) / 32, d = c->d;
+  return sizeof(uint32_t) * (ns * c->nodd * M + ns + cnt + 3 * (d + 1) * cnt);
+}
+
+#ifdef BCHFFT_EMU
+static const int kNtBig = 32;
+#else
+static const int kNtBig = 512;
+#endif
+
+// opt in to the large dynamic shared-memory carve-out (per device context)
+template <int M>
+static int ensure_attrs(bchfft_code *c)
+{
+  if (c->attr_set) return BCHFFT_OK;
+  BCHFFT_CUDA_TRY(cudaFuncSetAttribute(k_syndrome<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(227 * 1024)));
+  BCHFFT_CUDA_TRY(cudaFuncSetAttribute(k_locate<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(227 * 1024)));
+  c->attr_set = true;
+  return BCHFFT_OK;
+}
+
+template <int M>
+static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, const Scratch &s,
+                           cudaStream_t st)
+{
+  const unsigned ns = (unsigned)((cnt + 31) / 32);
+  const size_t smem = sizeof(uint32_t) * ((size_t)c->chunk_pos + c->chunk_pos / kSynSub + (size_t)c->nodd * M);
+  int rc0 = ensure_attrs<M>(c);
+  if (rc0) return rc0;
+  BCHFFT_LAUNCH(k_syndrome<M>, dim3(c->nchunks, ns), dim3(kNtBig), smem, st,
+                (const uint32_t *)d_words, c->wpc * 2u, c->length, (uint32_t)cnt, c->chunk_pos,
+                c->nodd, (const uint32_t *)c->d_taps, (const uint32_t *)c->d_fold, c->nsub_total,
+                s.acc, s.parity);
+  BCHFFT_CHECK_LAUNCH();
+  BCHFFT_LAUNCH(k_syn_finish<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
+                (const uint32_t *)s.acc, (const uint32_t *)s.parity, c->nodd, c->d, (uint32_t)cnt,
+                c->syn_fft_rule, s.syn, s.flag);
+  BCHFFT_CHECK_LAUNCH();
+  return BCHFFT_OK;
+}
+
+template <int M>
+static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t st)
+{
+  BCHFFT_LAUNCH(k_bm<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
+                (const uint32_t *)s.syn, (const int32_t *)s.flag, c->d, (uint32_t)cnt,
+                (const uint32_t *)c->f->d_exp, (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L);
+  BCHFFT_CHECK_LAUNCH();
+  return BCHFFT_OK;
+}
+
+// tcap: largest L that is located (t for bch_decode, d for the stage-level entry point)
+template <int M>
+static int launch_locate(bchfft_code *c, size_t cnt, const Scratch &s, uint32_t tcap, cudaStream_t st)
+{
+  const int K = ceil_log2u(tcap + 1u);
+  int t = c->f->t_max;
+  if (t > M) t = M;
+  while (t > K && sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K)) > (size_t)227 * 1024) t--;
+  if (K > t || K > M || sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K)) > (size_t)227 * 1024) {
+    set_error("bch locate: error-locator degree bound %u too large for one shared-memory tile", tcap);
+    return BCHFFT_ERR_UNSUPPORTED;
+  }
+  int rc0 = ensure_attrs<M>(c);
+  if (rc0) return rc0;
+  PassDesc fwd, bwd;
+  locate_descs(M, K, t, fwd, bwd);
+  const unsigned ns = (unsigned)((cnt + 31) / 32);
+  const size_t smem = sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K));
+  BCHFFT_LAUNCH(k_locate<M>, dim3(1u << (M - t), ns), dim3(kNtBig), smem, st,
+                (const uint32_t *)s.elp, (const uint32_t *)s.L, (const int32_t *)s.flag, c->d, tcap,
+                (uint32_t)cnt, c->f->tab, fwd, bwd, (const uint32_t *)c->f->d_log, s.count,
+                s.positions, s.pos_stride);
+  BCHFFT_CHECK_LAUNCH();
+  return BCHFFT_OK;
+}
+
+template <int M>
+static int decode_run(bchfft_code *c, uint64_t *d_words, size_t batch, uint8_t *d_ok,
+                      uint32_t *d_corrected, cudaStream_t st)
+{
+  const uint32_t pos_stride = c->t + 1u;
+  // chunk the batch so that the per-codeword intermediates stay L2-resident
+  const char *env = getenv("BCHFFT_DECODE_CHUNK");
+  size_t chunk = env ? (size_t)atol(env) : ((size_t)48 << 20) / (scratch_per_cw(c, pos_stride, M) + c->wpc * 8);
+  chunk = (chunk / 32) * 32;
+  if (chunk < 32) chunk = 32;
+  if (chunk > batch) chunk = batch;
+  if (chunk > (size_t)65535 * 32) chunk = (size_t)65535 * 32;
+  int rc = c->scratch.reserve(scratch_bytes(c, chunk, pos_stride, M));
+  if (rc) return rc;
+  for (size_t i0 = 0; i0 < batch; i0 += chunk) {
+    const size_t cnt = batch - i0 < chunk ? batch - i0 : chunk;
+    Scratch s;
+    carve(c, c->scratch.p, cnt, pos_stride, M, s);
+    BCHFFT_CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, zero_bytes(c, cnt, M), st));
+    uint64_t *w = d_words + i0 * c->wpc;
+    if ((rc = launch_syndrome<M>(c, w, cnt, s, st))) return rc;
+    if ((rc = launch_bm<M>(c, cnt, s, st))) return rc;
+    if ((rc = launch_locate<M>(c, cnt, s, c->t, st))) return rc;
+    BCHFFT_LAUNCH(k_correct, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, w, c->wpc,
+                  (uint32_t)cnt, (const int32_t *)s.flag, (const uint32_t *)s.L, c->t,
+                  (const uint32_t *)s.count, (const uint32_t *)s.positions, s.pos_stride,
+                  d_ok ? d_ok + i0 : (uint8_t *)nullptr, d_corrected ? d_corrected + i0 : (uint32_t *)nullptr);
+    BCHFFT_CHECK_LAUNCH();
+  }
+  return BCHFFT_OK;
+}
+
+// minimal polynomial of x^j over GF(2), as a bit mask (bit i = coefficient of X^i)
+static uint64_t minimal_poly(const bchfft_field *f, uint32_t j, int *deg_out)
+{
+  const uint32_t order = f->order;
+  const uint32_t *ex = f->h_exp.data(), *lg = f->h_log.data();
+  auto mul = [&](uint32_t a, uint32_t b) -> uint32_t {
+    if (!a || !b) return 0u;
+    uint32_t s = lg[a] + lg[b];
+    if (s >= order) s -= order;
+    return ex[s];
+  };
+  std::vector<uint32_t> p(1, 1u);
+  uint32_t e = j % order;
+  const uint32_t start = e;
+  do {
+    const uint32_t root = ex[e];
+    p.push_back(0u);
+    for (size_t i = p.size() - 1; i > 0; i--) p[i] = p[i - 1] ^ mul(p[i], root);
+    p[0] = mul(p[0], root);
+    e = (uint32_t)(((uint64_t)e * 2u) % order);
+  } while (e != start);
+  uint64_t mask = 0;
+  for (size_t i = 0; i < p.size(); i++)
+    if (p[i] & 1u) mask |= 1ull << i;
+  *deg_out = (int)p.size() - 1;
+  return mask;
+}
+
+}  // namespace bchfft
+
+using namespace bchfft;
+
+extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t length,
+                                  const uint64_t *packed_gen_poly, uint32_t gen_poly_degree,
+                                  bchfft_code **out)
+{
+  if (!f || !out) {
+    set_error("bchfft_code_create: null argument");
+    return BCHFFT_ERR_ARG;
+  }
+  *out = nullptr;
+  if (distance < 3 || !(distance & 1u) || length < 2 || length > f->n || distance >= length) {
+    set_error("bchfft_code_create: need odd distance >= 3 and distance < length <= 2^m");
+    return BCHFFT_ERR_ARG;
+  }
+  (void)packed_gen_poly;  // the decoder only needs the roots x^1..x^(d-1), not g itself
+  BCHFFT_CUDA_TRY(cudaSetDevice(f->device));
+  bchfft_code *c = new bchfft_code();
+  c->f = f;
+  c->d = distance;
+  c->t = (distance - 1u) / 2u;
+  c->length = length;
+  c->gen_degree = gen_poly_degree;
+  c->wpc = (length - 1u) / 64u + 1u;
+  c->nodd = c->t;
+  {
+    // method rule of bch_eval_syndrome (bch.c:240-254), float arithmetic as in the reference
+    const float threshold = 0.5f * f->m * f->m;
+    const float cost = ((float)distance) * ((float)gen_poly_degree) / ((float)f->n);
+    c->syn_fft_rule = cost > threshold ? 1u : 0u;
+  }
+  const uint32_t M = f->m, order = f->order;
+  const uint32_t npos = c->wpc * 64u;
+  if ((size_t)c->nodd * M * 4 + (size_t)(kSynSub + 1) * 4 > (size_t)200 * 1024) {
+    set_error("bchfft_code_create: t = %u too large for the shared-memory syndrome accumulators", c->t);
+    delete c;
+    return BCHFFT_ERR_UNSUPPORTED;
+  }
+  // position chunk per CTA: as much of the codeword as fits next to the accumulators
+  size_t budget = ((size_t)200 * 1024) / 4 - (size_t)c->nodd * M;
+  uint32_t chunk = 1u << 15;
+  while (chunk > (uint32_t)kSynSub && (chunk + chunk / kSynSub > budget || chunk / 2 >= npos)) chunk >>= 1;
+  c->chunk_pos = chunk;
+  c->nchunks = (npos + chunk - 1u) / chunk;
+  c->nsub_total = c->nchunks * (chunk / kSynSub);
+  std::vector<uint32_t> taps(c->nodd), fold((size_t)c->nodd * c->nsub_total * M);
+  for (uint32_t ji = 0; ji < c->nodd; ji++) {
+    const uint32_t j = 2u * ji + 1u;
+    int deg = 0;
+    const uint64_t mp = minimal_poly(f, j, &deg);
+    // Q_j = X^(M-deg) * M_j has degree exactly M; the LFSR taps are its low M coefficients
+    const uint64_t q = mp << (M - (uint32_t)deg);
+    taps[ji] = (uint32_t)(q & ((1ull << M) - 1ull));
+    for (uint32_t qg = 0; qg < c->nsub_total; qg++)
+      for (uint32_t b = 0; b < M; b++) {
+        const uint64_t e = ((uint64_t)j % order) * (((uint64_t)b + (uint64_t)qg * kSynSub) % order) % order;
+        fold[((size_t)ji * c->nsub_total + qg) * M + b] = f->h_exp[e];
+      }
+  }
+  cudaError_t e1 = cudaMalloc((void **)&c->d_taps, taps.size() * 4 + 16);
+  cudaError_t e2 = cudaMalloc((void **)&c->d_fold, fold.size() * 4 + 16);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    set_error("bchfft_code_create: cudaMalloc failed");
+    bchfft_code_destroy(c);
+    return BCHFFT_ERR_CUDA;
+  }
+  cudaMemcpy(c->d_taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(c->d_fold, fold.data(), fold.size() * 4, cudaMemcpyHostToDevice);
+  *out = c;
+  return BCHFFT_OK;
+}
+
+extern "C" void bchfft_code_destroy(bchfft_code *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->f->device);
+  cudaStreamSynchronize(c->f->stream);
+  cudaFree(c->d_taps);
+  cudaFree(c->d_fold);
+  c->scratch.release();
+  c->stage_words.release();
+  c->stage_ok.release();
+  c->stage_corr.release();
+  c->stage_a.release();
+  c->stage_b.release();
+  c->stage_c.release();
+  delete c;
+}
+
+#define BCHFFT_DISPATCH_M(m, CALL)                       \
+  switch (m) {                                           \
+    BCHFFT_M_LIST(CALL)                                  \
+    default:                                             \
+      set_error("unsupported field degree %u", (m));     \
+      return BCHFFT_ERR_UNSUPPORTED;                     \
+  }
+
+extern "C" int bchfft_bch_decode_dev(bchfft_code *c, uint64_t *d_words, size_t batch, uint8_t *d_ok,
+                                     uint32_t *d_corrected, void *stream)
+{
+  if (!c || !d_words) {
+    set_error("bchfft_bch_decode_dev: null argument");
+    return BCHFFT_ERR_ARG;
+  }
+  if (batch == 0) return BCHFFT_OK;
+  BCHFFT_CUDA_TRY(cudaSetDevice(c->f->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->f->stream;
+#define X(M) case M: return decode_run<M>(c, d_words, batch, d_ok, d_corrected, st);
+  BCHFFT_DISPATCH_M(c->f->m, X)
+#undef X
+}
+
+extern "C" int bchfft_bch_decode_host(bchfft_code *c, uint64_t *words, size_t batch, uint8_t *ok,
+                                      uint32_t *corrected)
+{
+  if (!c || !words) {
+    set_error("bchfft_bch_decode_host: null argument");
+    return BCHFFT_ERR_ARG;
+  }
+  if (batch == 0) return BCHFFT_OK;
+  BCHFFT_CUDA_TRY(cudaSetDevice(c->f->device));
+  cudaStream_t st = c->f->stream;
+  const size_t cw_bytes = (size_t)c->wpc * 8;
+  size_t per = ((size_t)256 << 20) / cw_bytes;
+  per = per < 32 ? 32 : (per / 32) * 32;
+  if (per > batch) per = batch;
+  int rc;
+  if ((rc = c->stage_words.reserve(per * cw_bytes))) return rc;
+  if ((rc = c->stage_ok.reserve(per))) return rc;
+  if ((rc = c->stage_corr.reserve(per * 4))) return rc;
+  for (size_t i0 = 0; i0 < batch; i0 += per) {
+    const size_t cnt = batch - i0 < per ? batch - i0 : per;
+    uint64_t *dw = (uint64_t *)c->stage_words.p;
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(dw, words + i0 * c->wpc, cnt * cw_bytes, cudaMemcpyHostToDevice, st));
+    rc = bchfft_bch_decode_dev(c, dw, cnt, (uint8_t *)c->stage_ok.p, (uint32_t *)c->stage_corr.p, st);
+    if (rc) return rc;
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(words + i0 * c->wpc, dw, cnt * cw_bytes, cudaMemcpyDeviceToHost, st));
+    if (ok) BCHFFT_CUDA_TRY(cudaMemcpyAsync(ok + i0, c->stage_ok.p, cnt, cudaMemcpyDeviceToHost, st));
+    if (corrected)
+      BCHFFT_CUDA_TRY(cudaMemcpyAsync(corrected + i0, c->stage_corr.p, cnt * 4, cudaMemcpyDeviceToHost, st));
+    BCHFFT_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return BCHFFT_OK;
+}
+
+// ---- stage-level entry points ---------------------------------------------------------------
+namespace bchfft {
+
+template <int M>
+static int syndrome_stage(bchfft_code *c, const uint64_t *words, size_t batch, uint32_t *syndromes,
+                          int32_t *flags)
+{
+  cudaStream_t st = c->f->stream;
+  const uint32_t pos_stride = c->d + 1u;
+  const size_t cw_bytes = (size_t)c->wpc * 8;
+  size_t per = ((size_t)64 << 20) / (cw_bytes + scratch_per_cw(c, pos_stride, M));
+  per = per < 32 ? 32 : (per / 32) * 32;
+  if (per > batch) per = batch;
+  int rc;
+  if ((rc = c->stage_words.reserve(per * cw_bytes))) return rc;
+  if ((rc = c->scratch.reserve(scratch_bytes(c, per, pos_stride, M)))) return rc;
+  for (size_t i0 = 0; i0 < batch; i0 += per) {
+    const size_t cnt = batch - i0 < per ? batch - i0 : per;
+    Scratch s;
+    carve(c, c->scratch.p, cnt, pos_stride, M, s);
+    BCHFFT_CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, zero_bytes(c, cnt, M), st));
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(c->stage_words.p, words + i0 * c->wpc, cnt * cw_bytes,
+                                    cudaMemcpyHostToDevice, st));
+    if ((rc = launch_syndrome<M>(c, (const uint64_t *)c->stage_words.p, cnt, s, st))) return rc;
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(syndromes + i0 * c->d, s.syn, cnt * c->d * 4, cudaMemcpyDeviceToHost, st));
+    if (flags) BCHFFT_CUDA_TRY(cudaMemcpyAsync(flags + i0, s.flag, cnt * 4, cudaMemcpyDeviceToHost, st));
+    BCHFFT_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return BCHFFT_OK;
+}
+
+template <int M>
+static int elp_stage(bchfft_code *c, const uint32_t *syndromes, size_t batch, uint32_t *elp, uint32_t *L)
+{
+  cudaStream_t st = c->f->stream;
+  const uint32_t pos_stride = c->d + 1u;
+  size_t per = ((size_t)64 << 20) / scratch_per_cw(c, pos_stride, M);
+  per = per < 32 ? 32 : (per / 32) * 32;
+  if (per > batch) per = batch;
+  int rc;
+  if ((rc = c->scratch.reserve(scratch_bytes(c, per, pos_stride, M)))) return rc;
+  std::vector<int32_t> ones(per, 1);
+  for (size_t i0 = 0; i0 < batch; i0 += per) {
+    const size_t cnt = batch - i0 < per ? batch - i0 : per;
+    Scratch s;
+    carve(c, c->scratch.p, cnt, pos_stride, M, s);
+    BCHFFT_CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, zero_bytes(c, cnt, M), st));
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.syn, syndromes + i0 * c->d, cnt * c->d * 4, cudaMemcpyHostToDevice, st));
+    // bch_compute_elp runs unconditionally when called directly
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.flag, ones.data(), cnt * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = launch_bm<M>(c, cnt, s, st))) return rc;
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(elp + i0 * (c->d + 1), s.elp, cnt * (c->d + 1) * 4, cudaMemcpyDeviceToHost, st));
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(L + i0, s.L, cnt * 4, cudaMemcpyDeviceToHost, st));
+    BCHFFT_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return BCHFFT_OK;
+}
+
+template <int M>
+static int locate_stage(bchfft_code *c, const uint32_t *elp, const uint32_t *L, size_t batch,
+                        uint32_t *positions, uint32_t *count)
+{
+  cudaStream_t st = c->f->stream;
+  const uint32_t pos_stride = c->d + 1u;
+  size_t per = ((size_t)64 << 20) / scratch_per_cw(c, pos_stride, M);
+  per = per < 32 ? 32 : (per / 32) * 32;
+  if (per > batch) per = batch;
+  int rc;
+  if ((rc = c->scratch.reserve(scratch_bytes(c, per, pos_stride, M)))) return rc;
+  std::vector<int32_t> ones(per, 1);
+  for (size_t i0 = 0; i0 < batch; i0 += per) {
+    const size_t cnt = batch - i0 < per ? batch - i0 : per;
+    Scratch s;
+    carve(c, c->scratch.p, cnt, pos_stride, M, s);
+    BCHFFT_CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, zero_bytes(c, cnt, M), st));
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.elp, elp + i0 * (c->d + 1), cnt * (c->d + 1) * 4, cudaMemcpyHostToDevice, st));
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.L, L + i0, cnt * 4, cudaMemcpyHostToDevice, st));
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.flag, ones.data(), cnt * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = launch_locate<M>(c, cnt, s, c->d, st))) return rc;
+    BCHFFT_LAUNCH(k_sort_positions, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, s.positions,
+                  s.pos_stride, (const uint32_t *)s.count, (uint32_t)cnt);
+    BCHFFT_CHECK_LAUNCH();
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(positions + i0 * pos_stride, s.positions, cnt * pos_stride * 4,
+                                    cudaMemcpyDeviceToHost, st));
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(count + i0, s.count, cnt * 4, cudaMemcpyDeviceToHost, st));
+    BCHFFT_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return BCHFFT_OK;
+}
+
+}  // namespace bchfft
+
+extern "C" int bchfft_bch_syndrome_host(bchfft_code *c, const uint64_t *words, size_t batch,
+                                        uint32_t *syndromes, int32_t *flags)
+{
+  if (!c || !words || !syndromes) {
+    set_error("bchfft_bch_syndrome_host: null argument");
+    return BCHFFT_ERR_ARG;
+  }
+  if (batch == 0) return BCHFFT_OK;
+  BCHFFT_CUDA_TRY(cudaSetDevice(c->f->device));
+#define X(M) case M: return syndrome_stage<M>(c, words, batch, syndromes, flags);
+  BCHFFT_DISPATCH_M(c->f->m, X)
+#undef X
+}
+
+extern "C" int bchfft_bch_elp_host(bchfft_code *c, const uint32_t *syndromes, size_t batch,
+                                   uint32_t *elp, uint32_t *L)
+{
+  if (!c || !syndromes || !elp || !L) {
+    set_error("bchfft_bch_elp_host: null argument");
+    return BCHFFT_ERR_ARG;
+  }
+  if (batch == 0) return BCHFFT_OK;
+  BCHFFT_CUDA_TRY(cudaSetDevice(c->f->device));
+#define X(M) case M: return elp_stage<M>(c, syndromes, batch, elp, L);
+  BCHFFT_DISPATCH_M(c->f->m, X)
+#undef X
+}
+
+extern "C" int bchfft_bch_locate_host(bchfft_code *c, const uint32_t *elp, const uint32_t *L,
+                                      size_t batch, uint32_t *positions, uint32_t *count)
+{
+  if (!c || !elp || !L || !positions || !count) {
+    set_error("bchfft_bch_locate_host: null argument");
+    return BCHFFT_ERR_ARG;
+  }
+  if (batch == 0) return BCHFFT_OK;
+  BCHFFT_CUDA_TRY(cudaSetDevice(c->f->device));
+#define X(M) case M: return locate_stage<M>(c, elp, L, batch, positions, count);
+  BCHFFT_DISPATCH_M(c->f->m, X)
+#undef X
+}

@@ -549,7 +549,12 @@ uint32_t orc_bch_decode(const orc_code *c, uint64_t *word, uint32_t *corrected)
       found = orc_bch_locate(c, elp, L, pos);
       if (found == L) {
         ok = 1;
-        for (uint32_t i = 0; i < found; i++) bit_flip(word, pos[i]);             /* :539-542 */
+        /* :539-542.  The bit-0 quirk reports position `order`; for a shortened code that
+         * bit lies outside the packed array and the reference's add_bit writes out of
+         * bounds (undefined behaviour).  Defined here as: counted, not flipped. */
+        const size_t nbits = orc_bch_words(c) * 64;
+        for (uint32_t i = 0; i < found; i++)
+          if (pos[i] < nbits) bit_flip(word, pos[i]);
       }
       free(pos);
     }

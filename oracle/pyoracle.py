@@ -343,21 +343,24 @@ class RefCode:
         cnt = self.lib.bch_locate_errors(C.byref(self.c), C.byref(self.buf), C.c_uint32(L))
         return np.ctypeslib.as_array(self.buf.m_error, (max(cnt, 1),))[:cnt].copy()
 
-    def decode(self, word):
-        w = np.ascontiguousarray(word, np.uint64).copy()
+    def _decode_one(self, word):
+        # Decode in a private buffer long enough for bit `order`: for shortened codes the
+        # reference's bit-0 quirk (bch.c:485 check commented out) flips a bit beyond the packed
+        # codeword; here that write lands in padding and is dropped.
+        pad = np.zeros(max(self.words, (1 << self.m) // 64 + 1), np.uint64)
+        pad[: self.words] = word
         self._zero_bm()
         corr = C.c_uint32(0)
-        ok = self.lib.bch_decode(C.byref(self.c), _p64(w), C.byref(self.buf), C.byref(corr))
-        return ok, corr.value, w
+        ok = self.lib.bch_decode(C.byref(self.c), _p64(pad), C.byref(self.buf), C.byref(corr))
+        return ok, corr.value, pad[: self.words].copy()
+
+    def decode(self, word):
+        return self._decode_one(np.ascontiguousarray(word, np.uint64))
 
     def decode_batch(self, words):
         w = np.ascontiguousarray(words, np.uint64).copy().reshape(-1, self.words)
         ok = np.zeros(w.shape[0], np.uint8)
         corr = np.zeros(w.shape[0], np.uint32)
         for i in range(w.shape[0]):
-            self._zero_bm()
-            c = C.c_uint32(0)
-            ok[i] = self.lib.bch_decode(C.byref(self.c), _p64(w[i]), C.byref(self.buf),
-                                        C.byref(c))
-            corr[i] = c.value
+            ok[i], corr[i], w[i] = self._decode_one(w[i])
         return ok, corr, w

@@ -1,0 +1,187 @@
+"""CPU-only execution of the REAL kernel sources (bch_fft_b200/csrc) by the fiber-based CUDA
+emulator in tools/cudaemu, checked against the oracle and the golden fixtures.  This is test
+infrastructure for a build container without a GPU: it validates index arithmetic, tiling
+schedules and the bitsliced field arithmetic before GPU time is spent.  The `-m gpu` tests
+repeat the same checks on the device through the nvcc-built library.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from bch_fft_b200 import _lib, api, synth
+from tests.common import GOLDEN, additive_input, decode_input, flip, fnv64
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _field(cabi, port, m):
+    exp, log = port.tables(m)
+    h = C.c_void_p()
+    _lib.check(cabi, cabi.bchfft_field_create(0, m, exp.ctypes.data, log.ctypes.data, C.byref(h)), "field")
+    return h
+
+
+def _fft(cabi, h, polys, terms):
+    B, n = polys.shape
+    res = np.full((B, n), 0xDEADBEEF, np.uint32)
+    nat = np.zeros((B, n), np.uint32)
+    _lib.check(cabi, cabi.bchfft_additive_fft_host(h, polys.ctypes.data, n, res.ctypes.data, n,
+                                                   nat.ctypes.data, n, terms, B), "fft")
+    assert (res[:, n - 1] == 0xDEADBEEF).all()      # entry n-1 is never written (additive_fft.c:20)
+    return res[:, : n - 1], nat
+
+
+@pytest.mark.parametrize("m", [4, 5, 8, 10, 13])
+def test_emu_additive_fft_vs_oracle(emu_libs, port, m):
+    cabi, _ = emu_libs
+    n = 1 << m
+    h = _field(cabi, port, m)
+    rng = np.random.default_rng(m)
+    for B, terms in ((1, n - 1), (33, n - 1), (3, 0), (3, 1), (3, 2), (5, 5), (34, n // 2 - 1),
+                     (2, n // 2), (2, n - 2), (2, n + 5)):
+        if m >= 12:
+            B = min(B, 2)
+        polys = rng.integers(0, n, (B, n), dtype=np.uint32)
+        res, nat = _fft(cabi, h, polys, terms)
+        for b in range(B):
+            o, c = port.additive_fft(m, polys[b], min(terms, n - 1))
+            assert (res[b] == o).all() and (nat[b] == c).all(), (m, B, terms, b)
+    cabi.bchfft_field_destroy(h)
+
+
+@pytest.mark.parametrize("rec", [r for r in GOLDEN["additive"] if r["m"] <= 13],
+                         ids=lambda r: f"m{r['m']}-terms{r['num_terms']}")
+def test_emu_additive_fft_golden(emu_libs, port, rec):
+    cabi, _ = emu_libs
+    h = _field(cabi, port, rec["m"])
+    res, nat = _fft(cabi, h, additive_input(rec)[None, :].copy(), rec["num_terms"])
+    assert f"{fnv64(res[0]):016x}" == rec["fnv_result"] and f"{fnv64(nat[0]):016x}" == rec["fnv_natural"]
+    cabi.bchfft_field_destroy(h)
+
+
+def test_emu_multi_pass_schedules(port):
+    """small tiles (BCHFFT_TMAX) force the multi-window pass schedule on small fields; run in a
+    subprocess because the tile size is read when the field context is created"""
+    code = (
+        "import sys, ctypes as C, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from bch_fft_b200 import _lib\n"
+        "from oracle.pyoracle import Port\n"
+        "P = Port(); cabi = _lib.bind(sys.argv[1]); rng = np.random.default_rng(9)\n"
+        "for m in (5, 7, 8, 10):\n"
+        "    n = 1 << m; exp, log = P.tables(m); h = C.c_void_p()\n"
+        "    assert cabi.bchfft_field_create(0, m, exp.ctypes.data, log.ctypes.data, C.byref(h)) == 0\n"
+        "    for B, terms in ((33, n - 1), (2, n // 2), (2, 3), (2, 0)):\n"
+        "        polys = rng.integers(0, n, (B, n), dtype=np.uint32)\n"
+        "        res = np.zeros((B, n), np.uint32)\n"
+        "        assert cabi.bchfft_additive_fft_host(h, polys.ctypes.data, n, res.ctypes.data, n, None, n, terms, B) == 0\n"
+        "        for b in range(B):\n"
+        "            assert (res[b, :n-1] == P.additive_fft(m, polys[b], terms)[0]).all(), (m, terms)\n"
+        "print('ok')\n")
+    emu = os.path.join(ROOT, "bch_fft_b200", "csrc", "libbchfft_emu.so")
+    for tmax in ("2", "3", "4", "6"):
+        env = dict(os.environ, BCHFFT_TMAX=tmax)
+        out = subprocess.run([sys.executable, "-c", code, emu], env=env, capture_output=True, text=True)
+        assert out.returncode == 0 and "ok" in out.stdout, (tmax, out.stderr[-2000:])
+
+
+def _words_for(pc, n, t, B, rng):
+    pool = [pc.encode(rng.integers(0, 2, n - pc.gen_degree, dtype=np.uint32)) for _ in range(4)]
+    words = np.zeros((B, pc.words), np.uint64)
+    for b in range(B):
+        w = pool[b % 4].copy()
+        ne = [0, 1, t, t // 2, t + 1, t + 2, t + 3][b % 7] if b < 56 else int(rng.integers(0, t + 1))
+        pos = rng.choice(n, min(ne, n), replace=False)
+        if b % 5 == 0 and ne:
+            pos[0] = 0                       # bit-0 quirk (bch.c:479-488)
+        for p in set(int(x) for x in pos):
+            flip(w, p)
+        words[b] = w
+    return words
+
+
+@pytest.mark.parametrize("n,t", [(15, 2), (63, 5), (255, 8), (255, 20), (1023, 10), (300, 3),
+                                 (5000, 12), (8191, 16), (8191, 64), (65535, 16)])
+def test_emu_bch_stages_and_decode_vs_oracle(emu_libs, port, n, t):
+    cabi, _ = emu_libs
+    pc = port.code(n, t)
+    h = _field(cabi, port, pc.m)
+    c = C.c_void_p()
+    _lib.check(cabi, cabi.bchfft_code_create(h, 2 * t + 1, n, pc.gen.ctypes.data, pc.gen_degree,
+                                             C.byref(c)), "code")
+    B = 70 if n < 2000 else 36
+    d = 2 * t + 1
+    words = _words_for(pc, n, t, B, np.random.default_rng(n + t))
+    syn = np.zeros((B, d), np.uint32)
+    flags = np.zeros(B, np.int32)
+    _lib.check(cabi, cabi.bchfft_bch_syndrome_host(c, words.ctypes.data, B, syn.ctypes.data,
+                                                   flags.ctypes.data), "syndrome")
+    elp = np.zeros((B, d + 1), np.uint32)
+    L = np.zeros(B, np.uint32)
+    _lib.check(cabi, cabi.bchfft_bch_elp_host(c, syn.ctypes.data, B, elp.ctypes.data, L.ctypes.data), "elp")
+    posn = np.zeros((B, d + 1), np.uint32)
+    cnt = np.zeros(B, np.uint32)
+    _lib.check(cabi, cabi.bchfft_bch_locate_host(c, elp.ctypes.data, L.ctypes.data, B,
+                                                 posn.ctypes.data, cnt.ctypes.data), "locate")
+    for b in range(B):
+        fl, s, used_fft = pc.syndrome(words[b])
+        assert (syn[b, 1:] == s[1:]).all()
+        if used_fft:
+            assert syn[b, 0] == s[0] and flags[b] == fl
+        Lr, er = pc.elp(syn[b])
+        assert L[b] == Lr and (elp[b, : Lr + 1] == er).all()
+        pr = pc.locate(elp[b, : Lr + 1], Lr)
+        assert cnt[b] == len(pr) and (posn[b, : cnt[b]] == pr).all()
+    ok = np.zeros(B, np.uint8)
+    corr = np.zeros(B, np.uint32)
+    out = words.copy()
+    _lib.check(cabi, cabi.bchfft_bch_decode_host(c, out.ctypes.data, B, ok.ctypes.data,
+                                                 corr.ctypes.data), "decode")
+    rok, rcorr, rw = pc.decode_batch(words)
+    assert (ok == rok).all() and (corr == rcorr).all() and (out == rw).all()
+    assert (ok == 0).any() and (ok == 1).any()
+    cabi.bchfft_code_destroy(c)
+    cabi.bchfft_field_destroy(h)
+
+
+@pytest.mark.parametrize("rec", [r for r in GOLDEN["decode"] if r["n"] <= 8191 and r["t"] <= 64],
+                         ids=lambda r: f"n{r['n']}-t{r['t']}")
+def test_emu_host_api_decode_golden(emu_libs, rec):
+    """through the reference-shaped host API (bch_gen_code / bch_encode / bch_decode_batch)"""
+    _, host = emu_libs
+    code = host.bch_gen_code(rec["n"], 2 * rec["t"] + 1)
+    grec = next(c for c in GOLDEN["codes"] if c["n"] == rec["n"] and c["t"] == rec["t"])
+    assert code.gen_degree == grec["gen_degree"] and f"{fnv64(code.gen):016x}" == grec["fnv_gen"]
+    pool, words = decode_input(rec, code.encode)
+    assert f"{fnv64(pool):016x}" == rec["fnv_pool"] and f"{fnv64(words):016x}" == rec["fnv_in"]
+    ok, corr, out = code.decode_batch(words)
+    assert [int(x) for x in ok] == rec["ok"] and [int(x) for x in corr] == rec["corrected"]
+    assert f"{fnv64(out):016x}" == rec["fnv_out"]
+    # single-word entry point agrees with the batch
+    for i in (0, 1, 2, len(words) - 1):
+        o, c, w = code.decode(words[i])
+        assert (o, c) == (rec["ok"][i], rec["corrected"][i]) and (w == out[i]).all()
+
+
+def test_emu_host_api_additive(emu_libs, port):
+    _, host = emu_libs
+    f = host.create_binary_finite_field(10)
+    exp, log = port.tables(10)
+    assert (f.exp == exp).all() and (f.log == log).all()
+    rng = np.random.default_rng(4)
+    poly = rng.integers(0, 1024, 1024, dtype=np.uint32)
+    want, want_nat = port.additive_fft(10, poly, 700)
+    p = poly.copy()
+    got = f.evaluate_polynomial_additive_FFT(p, 700)
+    assert (got == want).all() and (p == want_nat).all()     # p_poly clobbered like the reference
+    for variant in ("additive_DFT_opt", "additive_DFT", "additive_DFT_ref"):
+        p = poly.copy()
+        assert (f.additive_DFT(p, 700, variant) == want_nat).all()
+    polys = rng.integers(0, 1024, (5, 1024), dtype=np.uint32)
+    res = f.additive_fft_batch(polys, 1023)
+    for b in range(5):
+        assert (res[b] == port.additive_fft(10, polys[b], 1023)[0]).all()
