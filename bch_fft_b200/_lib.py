@@ -40,6 +40,10 @@ _SIGNATURES = {
     "bchfft_dev_free": (C.c_int, [C.c_int, _vp]),
     "bchfft_dev_upload": (C.c_int, [C.c_int, _vp, _vp, _sz]),
     "bchfft_dev_download": (C.c_int, [C.c_int, _vp, _vp, _sz]),
+    "bchfft_profile_begin": (C.c_int, []),
+    "bchfft_profile_end": (C.c_int, []),
+    "bchfft_profile_get": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_uint64)]),
     "bchfft_launch_count": (C.c_uint64, []),
     "bchfft_launch_count_reset": (None, []),
 }
@@ -73,6 +77,21 @@ def lib() -> C.CDLL:
                 "g.build()'` (nvcc, sm_100a).  bch_fft_b200 has no CPU fallback.")
         _lib = bind(CUDA_SO)
     return _lib
+
+
+def profile(l: C.CDLL, fn):
+    """run fn() with per-kernel timing; returns {kernel: (total_ms, launches)}"""
+    l.bchfft_profile_begin()
+    try:
+        fn()
+    finally:
+        n = l.bchfft_profile_end()
+    out = {}
+    for i in range(max(n, 0)):
+        name, ms, cnt = C.c_char_p(), C.c_double(), C.c_uint64()
+        l.bchfft_profile_get(i, C.byref(name), C.byref(ms), C.byref(cnt))
+        out[name.value.decode()] = (ms.value, cnt.value)
+    return out
 
 
 def check(l: C.CDLL, rc: int, what: str) -> None:

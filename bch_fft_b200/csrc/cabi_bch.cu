@@ -125,25 +125,22 @@ static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, 
   const size_t smem = sizeof(uint32_t) * ((size_t)c->chunk_pos + c->chunk_pos / kSynSub + (size_t)c->nodd * M);
   int rc0 = ensure_attrs<M>(c);
   if (rc0) return rc0;
-  BCHFFT_LAUNCH(k_syndrome<M>, dim3(c->nchunks, ns), dim3(kNtBig), smem, st,
+  BCHFFT_RUN(k_syndrome<M>, dim3(c->nchunks, ns), dim3(kNtBig), smem, st,
                 (const uint32_t *)d_words, c->wpc * 2u, c->length, (uint32_t)cnt, c->chunk_pos,
                 c->nodd, (const uint32_t *)c->d_taps, (const uint32_t *)c->d_fold, c->nsub_total,
                 s.acc, s.parity);
-  BCHFFT_CHECK_LAUNCH();
-  BCHFFT_LAUNCH(k_syn_finish<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
+  BCHFFT_RUN(k_syn_finish<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
                 (const uint32_t *)s.acc, (const uint32_t *)s.parity, c->nodd, c->d, (uint32_t)cnt,
                 c->syn_fft_rule, s.syn, s.flag);
-  BCHFFT_CHECK_LAUNCH();
   return BCHFFT_OK;
 }
 
 template <int M>
 static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t st)
 {
-  BCHFFT_LAUNCH(k_bm<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
+  BCHFFT_RUN(k_bm<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
                 (const uint32_t *)s.syn, (const int32_t *)s.flag, c->d, (uint32_t)cnt,
                 (const uint32_t *)c->f->d_exp, (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L);
-  BCHFFT_CHECK_LAUNCH();
   return BCHFFT_OK;
 }
 
@@ -165,11 +162,10 @@ static int launch_locate(bchfft_code *c, size_t cnt, const Scratch &s, uint32_t 
   locate_descs(M, K, t, fwd, bwd);
   const unsigned ns = (unsigned)((cnt + 31) / 32);
   const size_t smem = sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K));
-  BCHFFT_LAUNCH(k_locate<M>, dim3(1u << (M - t), ns), dim3(kNtBig), smem, st,
+  BCHFFT_RUN(k_locate<M>, dim3(1u << (M - t), ns), dim3(kNtBig), smem, st,
                 (const uint32_t *)s.elp, (const uint32_t *)s.L, (const int32_t *)s.flag, c->d, tcap,
                 (uint32_t)cnt, c->f->tab, fwd, bwd, (const uint32_t *)c->f->d_log, s.count,
                 s.positions, s.pos_stride);
-  BCHFFT_CHECK_LAUNCH();
   return BCHFFT_OK;
 }
 
@@ -196,11 +192,10 @@ static int decode_run(bchfft_code *c, uint64_t *d_words, size_t batch, uint8_t *
     if ((rc = launch_syndrome<M>(c, w, cnt, s, st))) return rc;
     if ((rc = launch_bm<M>(c, cnt, s, st))) return rc;
     if ((rc = launch_locate<M>(c, cnt, s, c->t, st))) return rc;
-    BCHFFT_LAUNCH(k_correct, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, w, c->wpc,
+    BCHFFT_RUN(k_correct, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, w, c->wpc,
                   (uint32_t)cnt, (const int32_t *)s.flag, (const uint32_t *)s.L, c->t,
                   (const uint32_t *)s.count, (const uint32_t *)s.positions, s.pos_stride,
                   d_ok ? d_ok + i0 : (uint8_t *)nullptr, d_corrected ? d_corrected + i0 : (uint32_t *)nullptr);
-    BCHFFT_CHECK_LAUNCH();
   }
   return BCHFFT_OK;
 }
@@ -450,6 +445,10 @@ static int locate_stage(bchfft_code *c, const uint32_t *elp, const uint32_t *L, 
   int rc;
   if ((rc = c->scratch.reserve(scratch_bytes(c, per, pos_stride, M)))) return rc;
   std::vector<int32_t> ones(per, 1);
+  // the FFT is sized for the largest degree actually requested (bch.c:406: p_elp_degree)
+  uint32_t lmax = 1;
+  for (size_t i = 0; i < batch; i++)
+    if (L[i] > lmax && L[i] <= c->d) lmax = L[i];
   for (size_t i0 = 0; i0 < batch; i0 += per) {
     const size_t cnt = batch - i0 < per ? batch - i0 : per;
     Scratch s;
@@ -458,10 +457,9 @@ static int locate_stage(bchfft_code *c, const uint32_t *elp, const uint32_t *L, 
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.elp, elp + i0 * (c->d + 1), cnt * (c->d + 1) * 4, cudaMemcpyHostToDevice, st));
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.L, L + i0, cnt * 4, cudaMemcpyHostToDevice, st));
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.flag, ones.data(), cnt * 4, cudaMemcpyHostToDevice, st));
-    if ((rc = launch_locate<M>(c, cnt, s, c->d, st))) return rc;
-    BCHFFT_LAUNCH(k_sort_positions, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, s.positions,
+    if ((rc = launch_locate<M>(c, cnt, s, lmax, st))) return rc;
+    BCHFFT_RUN(k_sort_positions, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, s.positions,
                   s.pos_stride, (const uint32_t *)s.count, (uint32_t)cnt);
-    BCHFFT_CHECK_LAUNCH();
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(positions + i0 * pos_stride, s.positions, cnt * pos_stride * 4,
                                     cudaMemcpyDeviceToHost, st));
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(count + i0, s.count, cnt * 4, cudaMemcpyDeviceToHost, st));

@@ -26,8 +26,16 @@ extern uint64_t g_launches;
     }                                                                                      \
   } while (0)
 
-#define BCHFFT_CHECK_LAUNCH()                                                              \
+// per-kernel device timing (see bchfft_profile_begin): events around a launch while enabled
+void prof_before(const char *kernel_name, cudaStream_t stream);
+void prof_after();
+
+// launch + bookkeeping: counts the launch, times it when profiling, surfaces launch errors
+#define BCHFFT_RUN(kernel, grid, block, smem, stream, ...)                                 \
   do {                                                                                     \
+    bchfft::prof_before(#kernel, (stream));                                                \
+    BCHFFT_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__);                         \
+    bchfft::prof_after();                                                                  \
     bchfft::g_launches++;                                                                  \
     BCHFFT_CUDA_TRY(cudaGetLastError());                                                   \
   } while (0)

@@ -36,6 +36,39 @@ void DeviceBuffer::release()
   bytes = 0;
 }
 
+// ---- per-kernel profiling -------------------------------------------------------------------
+struct ProfRec {
+  const char *name;
+  cudaEvent_t a, b;
+};
+static bool g_prof = false;
+static std::vector<ProfRec> g_prof_recs;
+static cudaStream_t g_prof_stream = nullptr;
+struct ProfSum {
+  std::string name;
+  double ms = 0.0;
+  uint64_t launches = 0;
+};
+static std::vector<ProfSum> g_prof_sums;
+
+void prof_before(const char *kernel_name, cudaStream_t stream)
+{
+  if (!g_prof) return;
+  ProfRec r;
+  r.name = kernel_name;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, stream);
+  g_prof_stream = stream;
+  g_prof_recs.push_back(r);
+}
+
+void prof_after()
+{
+  if (!g_prof || g_prof_recs.empty()) return;
+  cudaEventRecord(g_prof_recs.back().b, g_prof_stream);
+}
+
 template <class T>
 static int upload_vec(const std::vector<T> &v, T **out)
 {
@@ -69,6 +102,50 @@ extern "C" int bchfft_device_count(void)
     return BCHFFT_ERR_CUDA;
   }
   return n;
+}
+
+extern "C" int bchfft_profile_begin(void)
+{
+  g_prof_recs.clear();
+  g_prof_sums.clear();
+  g_prof = true;
+  return BCHFFT_OK;
+}
+
+extern "C" int bchfft_profile_end(void)
+{
+  g_prof = false;
+  BCHFFT_CUDA_TRY(cudaDeviceSynchronize());
+  for (auto &r : g_prof_recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+    std::string nm(r.name);
+    const size_t lt = nm.find('<');
+    if (lt != std::string::npos) nm = nm.substr(0, lt);
+    ProfSum *slot = nullptr;
+    for (auto &s : g_prof_sums)
+      if (s.name == nm) slot = &s;
+    if (!slot) {
+      g_prof_sums.push_back(ProfSum());
+      slot = &g_prof_sums.back();
+      slot->name = nm;
+    }
+    slot->ms += ms;
+    slot->launches++;
+  }
+  g_prof_recs.clear();
+  return (int)g_prof_sums.size();
+}
+
+extern "C" int bchfft_profile_get(int idx, const char **name, double *total_ms, uint64_t *launches)
+{
+  if (idx < 0 || idx >= (int)g_prof_sums.size()) return BCHFFT_ERR_ARG;
+  if (name) *name = g_prof_sums[idx].name.c_str();
+  if (total_ms) *total_ms = g_prof_sums[idx].ms;
+  if (launches) *launches = g_prof_sums[idx].launches;
+  return BCHFFT_OK;
 }
 
 extern "C" uint64_t bchfft_launch_count(void) { return g_launches; }

@@ -55,9 +55,8 @@ static int fft_run(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride,
     const uint32_t *src = d_polys + s0 * 32 * poly_stride;
     {
       dim3 grid((unsigned)((((size_t)1 << K) + nt_io - 1) / nt_io), (unsigned)cs);
-      BCHFFT_LAUNCH(k_bitslice_in<M>, grid, dim3(nt_io), 0, stream, src, poly_stride, items, ncoef,
+      BCHFFT_RUN(k_bitslice_in<M>, grid, dim3(nt_io), 0, stream, src, poly_stride, items, ncoef,
                     (uint32_t)K, bufF);
-      BCHFFT_CHECK_LAUNCH();
     }
     for (size_t pi = 0; pi < plan.passes.size(); pi++) {
       const PassDesc &pd = plan.passes[pi];
@@ -69,23 +68,20 @@ static int fft_run(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride,
       const size_t dst_words = bw ? bwd_words : fwd_words;
       dim3 grid(1u << (pd.dom_bits - pd.t), (unsigned)cs);
       const size_t smem = ((size_t)4 * M) << pd.t;
-      BCHFFT_LAUNCH(k_gm_pass<M>, grid, dim3(nt_pass), smem, stream, psrc, pdst, src_words,
+      BCHFFT_RUN(k_gm_pass<M>, grid, dim3(nt_pass), smem, stream, psrc, pdst, src_words,
                     dst_words, f->tab, pd);
-      BCHFFT_CHECK_LAUNCH();
     }
     if (d_results) {
       dim3 grid((n - 1u + nt_io - 1) / nt_io, (unsigned)cs);
-      BCHFFT_LAUNCH(k_gather_out<M>, grid, dim3(nt_io), 0, stream, (const uint32_t *)bufB, bwd_words,
+      BCHFFT_RUN(k_gather_out<M>, grid, dim3(nt_io), 0, stream, (const uint32_t *)bufB, bwd_words,
                     (const uint32_t *)f->d_perm_exp, n - 1u, d_results + s0 * 32 * result_stride,
                     result_stride, items);
-      BCHFFT_CHECK_LAUNCH();
     }
     if (d_natural) {
       dim3 grid((n + nt_io - 1) / nt_io, (unsigned)cs);
-      BCHFFT_LAUNCH(k_gather_out<M>, grid, dim3(nt_io), 0, stream, (const uint32_t *)bufB, bwd_words,
+      BCHFFT_RUN(k_gather_out<M>, grid, dim3(nt_io), 0, stream, (const uint32_t *)bufB, bwd_words,
                     (const uint32_t *)f->d_perm_nat, n, d_natural + s0 * 32 * natural_stride,
                     natural_stride, items);
-      BCHFFT_CHECK_LAUNCH();
     }
   }
   return BCHFFT_OK;

@@ -122,6 +122,15 @@ int bchfft_dev_download(int device, void *h_dst, const void *d_src, size_t bytes
 uint64_t bchfft_launch_count(void);
 void bchfft_launch_count_reset(void);
 
+/* per-kernel device timing: between begin and end every kernel launch of this library is
+ * bracketed by CUDA events on its stream.  bchfft_profile_end() synchronises the device,
+ * returns the number of distinct kernels seen; bchfft_profile_get(i, ...) reads kernel i's
+ * name, summed device time and launch count.  (bench.py uses it for the roofline of the
+ * dominant kernel; keep it off in timed regions.) */
+int bchfft_profile_begin(void);
+int bchfft_profile_end(void);
+int bchfft_profile_get(int idx, const char **name, double *total_ms, uint64_t *launches);
+
 #ifdef __cplusplus
 }
 #endif

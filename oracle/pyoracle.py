@@ -236,7 +236,23 @@ class Ref:
         L.bch_compute_elp.restype = C.c_uint32
         L.bch_locate_errors.restype = C.c_uint32
         L.bch_eval_syndrome.restype = C.c_int32
+        L.ref_bch_decode_batch_mt.restype = C.c_double
+        L.ref_bch_decode_batch_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                              C.c_void_p, C.c_int]
+        L.ref_additive_fft_batch_mt.restype = C.c_double
+        L.ref_additive_fft_batch_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                C.c_size_t, C.c_int]
         self._fields = {}
+
+    def additive_fft_batch_mt(self, m, polys, num_terms, nthreads):
+        """multi-threaded batch through the reference's evaluate_polynomial_additive_FFT;
+        returns (results[B, n-1], wall seconds)"""
+        n = 1 << m
+        p = np.ascontiguousarray(polys, np.uint32).copy().reshape(-1, n)
+        out = np.zeros_like(p)
+        dt = self.lib.ref_additive_fft_batch_mt(C.byref(self.field(m)), p.ctypes.data,
+                                                out.ctypes.data, num_terms, p.shape[0], nthreads)
+        return out[:, : n - 1], dt
 
     def field(self, m):
         if m not in self._fields:
@@ -356,6 +372,17 @@ class RefCode:
 
     def decode(self, word):
         return self._decode_one(np.ascontiguousarray(word, np.uint64))
+
+    def decode_batch_mt(self, words, nthreads):
+        """multi-threaded batch through the reference's bch_decode (full-length codes only: no
+        padding per word); returns (ok, corrected, words, wall seconds)"""
+        assert self.words * 64 > (1 << self.m) - 1, "shortened code: use decode_batch"
+        w = np.ascontiguousarray(words, np.uint64).copy().reshape(-1, self.words)
+        ok = np.zeros(w.shape[0], np.uint8)
+        corr = np.zeros(w.shape[0], np.uint32)
+        dt = self.lib.ref_bch_decode_batch_mt(C.byref(self.c), w.ctypes.data, w.shape[0],
+                                              ok.ctypes.data, corr.ctypes.data, nthreads)
+        return ok, corr, w, dt
 
     def decode_batch(self, words):
         w = np.ascontiguousarray(words, np.uint64).copy().reshape(-1, self.words)

@@ -1,0 +1,284 @@
+"""Parity tests proper: the CUDA path (through the C-ABI and through the drop-in host library)
+against the oracle on seeded inputs, against the golden fixtures produced by the unmodified
+reference, and -- at BASELINE.json's full sizes -- through size-independent properties.
+Everything here is bit-exact (integer / GF(2^m) work)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bch_fft_b200 import _lib, api, synth
+from tests.common import GOLDEN, additive_input, decode_input, flip, fnv64
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _field(cabi, port, m):
+    exp, log = port.tables(m)
+    h = C.c_void_p()
+    _lib.check(cabi, cabi.bchfft_field_create(0, m, exp.ctypes.data, log.ctypes.data, C.byref(h)), "field")
+    return h
+
+
+def _fft(cabi, h, polys, terms, natural=True):
+    B, n = polys.shape
+    res = np.full((B, n), 0xDEADBEEF, np.uint32)
+    nat = np.zeros((B, n), np.uint32) if natural else None
+    _lib.check(cabi, cabi.bchfft_additive_fft_host(h, polys.ctypes.data, n, res.ctypes.data, n,
+                                                   nat.ctypes.data if natural else None, n, terms, B), "fft")
+    assert (res[:, n - 1] == 0xDEADBEEF).all()
+    return res[:, : n - 1], nat
+
+
+def test_native_library_is_loaded(gpu_libs):
+    cabi, host = gpu_libs
+    assert cabi.bchfft_is_emulated() == 0 and cabi.bchfft_device_count() >= 1
+    maps = open("/proc/self/maps").read()
+    assert "libbchfft_cuda.so" in maps and "libbchfft_emu.so" not in maps
+
+
+@pytest.mark.parametrize("m", [4, 8, 10, 13, 16])
+def test_additive_fft_vs_oracle(gpu_libs, port, m):
+    cabi, _ = gpu_libs
+    n = 1 << m
+    h = _field(cabi, port, m)
+    rng = np.random.default_rng(100 + m)
+    for B, terms in ((1, n - 1), (33, n - 1), (64, n - 1), (3, 0), (3, 1), (3, 2), (5, 5),
+                     (34, n // 2 - 1), (7, n // 2), (2, n - 2), (2, n + 5), (5, 100 % n), (5, 1000 % n)):
+        polys = rng.integers(0, n, (B, n), dtype=np.uint32)
+        res, nat = _fft(cabi, h, polys, terms)
+        check = range(B) if m <= 13 else sorted({0, B // 2, B - 1})
+        for b in check:
+            o, c = port.additive_fft(m, polys[b], min(terms, n - 1))
+            assert (res[b] == o).all() and (nat[b] == c).all(), (m, B, terms, b)
+    cabi.bchfft_field_destroy(h)
+
+
+@pytest.mark.parametrize("rec", GOLDEN["additive"], ids=lambda r: f"m{r['m']}-terms{r['num_terms']}")
+def test_additive_fft_golden(gpu_libs, port, rec):
+    cabi, _ = gpu_libs
+    h = _field(cabi, port, rec["m"])
+    res, nat = _fft(cabi, h, additive_input(rec)[None, :].copy(), rec["num_terms"])
+    assert f"{fnv64(res[0]):016x}" == rec["fnv_result"] and f"{fnv64(nat[0]):016x}" == rec["fnv_natural"]
+    assert [int(x) for x in res[0, :8]] == rec["head"]
+    cabi.bchfft_field_destroy(h)
+
+
+def test_additive_fft_gf2_20_batch(gpu_libs, port):
+    """BASELINE configs[3]: GF(2^20), transform larger than one SM's tile (multi-pass schedule)"""
+    cabi, _ = gpu_libs
+    m, n, B = 20, 1 << 20, 34
+    h = _field(cabi, port, m)
+    polys = synth.random_polys(m, B, 0xC4)
+    res, _ = _fft(cabi, h, polys, n - 1, natural=False)
+    for b in (0, 33):
+        assert (res[b] == port.additive_fft(m, polys[b], n - 1)[0]).all()
+    # linearity across the batch (size-independent property): FFT(a ^ b) = FFT(a) ^ FFT(b)
+    mix = (polys[1] ^ polys[2])[None, :].copy()
+    r2, _ = _fft(cabi, h, mix, n - 1, natural=False)
+    assert (r2[0] == (res[1] ^ res[2])).all()
+    cabi.bchfft_field_destroy(h)
+
+
+def test_additive_fft_full_batch_properties(gpu_libs, port):
+    """BASELINE configs[0] batched at full size (4096 polynomials over GF(2^16), 1 GiB):
+    spot parity against the oracle + linearity + batch-position independence"""
+    cabi, _ = gpu_libs
+    m, n, B = 16, 1 << 16, 4096
+    h = _field(cabi, port, m)
+    polys = synth.random_polys(m, B, 0xC1)
+    polys[7] = polys[5] ^ polys[6]
+    polys[4095] = polys[3]
+    res, _ = _fft(cabi, h, polys, n - 1, natural=False)
+    for b in (0, 31, 32, 2047, 4095):
+        assert (res[b] == port.additive_fft(m, polys[b], n - 1)[0]).all(), b
+    assert (res[7] == (res[5] ^ res[6])).all()
+    assert (res[4095] == res[3]).all()
+    cabi.bchfft_field_destroy(h)
+
+
+def _words_for(pc, n, t, B, rng):
+    pool = [pc.encode(rng.integers(0, 2, n - pc.gen_degree, dtype=np.uint32)) for _ in range(4)]
+    words = np.zeros((B, pc.words), np.uint64)
+    for b in range(B):
+        w = pool[b % 4].copy()
+        ne = [0, 1, t, t // 2, t + 1, t + 2, t + 3][b % 7] if b < 56 else int(rng.integers(0, t + 1))
+        pos = rng.choice(n, min(ne, n), replace=False)
+        if b % 5 == 0 and ne:
+            pos[0] = 0
+        for p in set(int(x) for x in pos):
+            flip(w, p)
+        words[b] = w
+    return words
+
+
+@pytest.mark.parametrize("n,t", [(15, 2), (63, 5), (255, 8), (255, 20), (1023, 10), (300, 3), (5000, 12),
+                                 (8191, 8), (8191, 16), (8191, 64), (8191, 200), (65535, 16),
+                                 (65535, 100), (65535, 1000)])
+def test_bch_stages_and_decode_vs_oracle(gpu_libs, port, n, t):
+    cabi, _ = gpu_libs
+    pc = port.code(n, t)
+    h = _field(cabi, port, pc.m)
+    c = C.c_void_p()
+    _lib.check(cabi, cabi.bchfft_code_create(h, 2 * t + 1, n, pc.gen.ctypes.data, pc.gen_degree,
+                                             C.byref(c)), "code")
+    B = 100 if t <= 200 else 40
+    d = 2 * t + 1
+    words = _words_for(pc, n, t, B, np.random.default_rng(n + t))
+    syn = np.zeros((B, d), np.uint32)
+    flags = np.zeros(B, np.int32)
+    _lib.check(cabi, cabi.bchfft_bch_syndrome_host(c, words.ctypes.data, B, syn.ctypes.data,
+                                                   flags.ctypes.data), "syndrome")
+    elp = np.zeros((B, d + 1), np.uint32)
+    L = np.zeros(B, np.uint32)
+    _lib.check(cabi, cabi.bchfft_bch_elp_host(c, syn.ctypes.data, B, elp.ctypes.data, L.ctypes.data), "elp")
+    posn = np.zeros((B, d + 1), np.uint32)
+    cnt = np.zeros(B, np.uint32)
+    _lib.check(cabi, cabi.bchfft_bch_locate_host(c, elp.ctypes.data, L.ctypes.data, B,
+                                                 posn.ctypes.data, cnt.ctypes.data), "locate")
+    for b in range(B):
+        fl, s, used_fft = pc.syndrome(words[b])
+        assert (syn[b, 1:] == s[1:]).all()
+        if used_fft:
+            assert syn[b, 0] == s[0] and flags[b] == fl
+        Lr, er = pc.elp(syn[b])
+        assert L[b] == Lr and (elp[b, : Lr + 1] == er).all()
+        pr = pc.locate(elp[b, : Lr + 1], Lr)
+        assert cnt[b] == len(pr) and (posn[b, : cnt[b]] == pr).all()
+    ok = np.zeros(B, np.uint8)
+    corr = np.zeros(B, np.uint32)
+    out = words.copy()
+    _lib.check(cabi, cabi.bchfft_bch_decode_host(c, out.ctypes.data, B, ok.ctypes.data,
+                                                 corr.ctypes.data), "decode")
+    rok, rcorr, rw = pc.decode_batch(words)
+    assert (ok == rok).all() and (corr == rcorr).all() and (out == rw).all()
+    cabi.bchfft_code_destroy(c)
+    cabi.bchfft_field_destroy(h)
+
+
+@pytest.mark.parametrize("rec", GOLDEN["decode"], ids=lambda r: f"n{r['n']}-t{r['t']}")
+def test_host_api_decode_golden(gpu_libs, rec):
+    """reference-shaped host API (bch_gen_code / bch_encode / bch_decode[_batch]) against the
+    fixtures generated by the unmodified reference"""
+    _, host = gpu_libs
+    code = host.bch_gen_code(rec["n"], 2 * rec["t"] + 1)
+    grec = next(c for c in GOLDEN["codes"] if c["n"] == rec["n"] and c["t"] == rec["t"])
+    assert code.gen_degree == grec["gen_degree"] and f"{fnv64(code.gen):016x}" == grec["fnv_gen"]
+    pool, words = decode_input(rec, code.encode)
+    assert f"{fnv64(pool):016x}" == rec["fnv_pool"] and f"{fnv64(words):016x}" == rec["fnv_in"]
+    ok, corr, out = code.decode_batch(words)
+    assert [int(x) for x in ok] == rec["ok"] and [int(x) for x in corr] == rec["corrected"]
+    assert f"{fnv64(out):016x}" == rec["fnv_out"]
+    for i in (0, 1, 2, len(words) - 1):
+        o, c, w = code.decode(words[i])
+        assert (o, c) == (rec["ok"][i], rec["corrected"][i]) and (w == out[i]).all()
+
+
+def test_host_api_additive_single_call(gpu_libs, port):
+    """evaluate_polynomial_additive_FFT / additive_DFT* drop-in semantics (additive_fft.c:13-21)"""
+    _, host = gpu_libs
+    f = host.create_binary_finite_field(16)
+    poly = synth.demo_poly(16)
+    p = poly.copy()
+    got = f.evaluate_polynomial_additive_FFT(p, (1 << 16) - 1)
+    assert fnv64(got) == 0xda6143e12631d2df and fnv64(p) == 0x4ce7d70654a732f3   # Appendix C
+    rng = np.random.default_rng(4)
+    poly = rng.integers(0, 1 << 16, 1 << 16, dtype=np.uint32)
+    want_nat = port.additive_fft(16, poly, 700)[1]
+    for variant in ("additive_DFT_opt", "additive_DFT", "additive_DFT_ref"):
+        p = poly.copy()
+        assert (f.additive_DFT(p, 700, variant) == want_nat).all()
+
+
+def test_decode_full_batch_properties(gpu_libs, port):
+    """BASELINE configs[2] at full size (10^6 words, n=8191, t=16): encode -> corrupt -> decode
+    round trip.  Every word with <= t distinct errors (none at bit 0) must come back equal to its
+    clean codeword with corrected = #errors; decoding twice is idempotent; a 20000-word sample is
+    compared field by field with the oracle."""
+    _, host = gpu_libs
+    n, t, B = 8191, 16, 1_000_000
+    code = host.bch_gen_code(n, 2 * t + 1)
+    bits = (synth.splitmix64(0xC3, 64 * code.data_bits) & np.uint64(1)).astype(np.uint32)
+    pool = np.stack([code.encode(b) for b in bits.reshape(64, -1)])
+    # rebuild the same words without errors: same seed, t = 0 draws nothing
+    r = synth.splitmix64(0xC3, B * 6).reshape(B, 6)
+    clean = np.zeros((B, code.words), np.uint64)
+    for k in range(4):
+        clean ^= pool[(r[:, k] % np.uint64(64)).astype(np.int64)]
+    words, nerr = synth.corrupt_codewords(pool, n, t, B, 0xC3, beyond_fraction=0.01)
+    diff = words ^ clean
+    ok, corr, out = code.decode_batch(words)
+    assert [int(x) for x in ok] == rec["ok"] and [int(x) for x in corr] == rec["corrected"]
+    assert f"{fnv64(out):016x}" == rec["fnv_out"]
+    for i in (0, 1, 2, len(words) - 1):
+        o, c, w = code.decode(words[i])
+        assert (o, c) == (rec["ok"][i], rec["corrected"][i]) and (w == out[i]).all()
+
+
+def test_host_api_additive_single_call(gpu_libs, port):
+    """evaluate_polynomial_additive_FFT / additive_DFT* drop-in semantics (additive_fft.c:13-21)"""
+    _, host = gpu_libs
+    f = host.create_binary_finite_field(16)
+    poly = synth.demo_poly(16)
+    p = poly.copy()
+    got = f.evaluate_polynomial_additive_FFT(p, (1 << 16) - 1)
+    assert fnv64(got) == 0xda6143e12631d2df and fnv64(p) == 0x4ce7d70654a732f3   # Appendix C
+    rng = np.random.default_rng(4)
+    poly = rng.integers(0, 1 << 16, 1 << 16, dtype=np.uint32)
+    want_nat = port.additive_fft(16, poly, 700)[1]
+    for variant in ("additive_DFT_opt", "additive_DFT", "additive_DFT_ref"):
+        p = poly.copy()
+        assert (f.additive_DFT(p, 700, variant) == want_nat).all()
+
+
+def test_decode_full_batch_properties(gpu_libs, port):
+    """BASELINE configs[2] at full size (10^6 words, n=8191, t=16): encode -> corrupt -> decode
+    round trip.  Every word with <= t distinct errors (none at bit 0) must come back equal to its
+    clean codeword with corrected = #errors; decoding twice is idempotent; a 20000-word sample is
+    compared field by field with the oracle."""
+    _, host = gpu_libs
+    n, t, B = 8191, 16, 1_000_000
+    code = host.bch_gen_code(n, 2 * t + 1)
+    bits = (synth.splitmix64(0xC3, 64 * code.data_bits) & np.uint64(1)).astype(np.uint32)
+    pool = np.stack([code.encode(b) for b in bits.reshape(64, -1)])
+    # rebuild the same words without errors: same seed, t = 0 draws nothing
+    r = synth.splitmix64(0xC3, B * 6).reshape(B, 6)
+    clean = np.zeros((B, code.words), np.uint64)
+    for k in range(4):
+        clean ^= pool[(r[:, k] % np.uint64(64)).astype(np.int64)]
+    words, nerr = synth.corrupt_codewords(pool, n, t, B, 0xC3, beyond_fraction=0.01)
+    diff = words ^ clean
+    weight = np.zeros(B, np.int64)
+    for k in range(code.words):
+        weight += np.array([bin(int(x)).count("1") for x in diff[:20000, k]] + [0] * 0, dtype=np.int64) \
+            if False else 0
+    ok, corr, out = code.decode_batch(words)
+    sample = 20000
+    pc = port.code(n, t)
+    rok, rcorr, rout = pc.decode_batch(words[:sample])
+    assert (ok[:sample] == rok).all() and (corr[:sample] == rcorr).all() and (out[:sample] == rout).all()
+    # round trip on the full batch
+    bit0 = (diff[:, 0] & np.uint64(1)) != 0
+    tbl = np.array([bin(i).count("1") for i in range(256)], np.uint8)
+    popc = tbl[diff.view(np.uint8).reshape(B, -1)].sum(axis=1, dtype=np.int64)
+    good = (popc <= t) & ~bit0
+    assert good.sum() > 0.9 * B
+    assert (ok[good] == 1).all() and (corr[good] == popc[good]).all()
+    assert (out[good] == clean[good]).all()
+    assert (out[ok == 0] == words[ok == 0]).all()            # failures leave the word untouched
+    ok2, corr2, out2 = code.decode_batch(out[good][:200000])
+    assert (ok2 == 1).all() and (corr2 == 0).all() and (out2 == out[good][:200000]).all()
+
+
+def test_reference_demo_sources_build_and_pass(gpu_libs):
+    """the reference's bchdemo source, UNCHANGED, linked against our libraries (drop-in check);
+    needs the reference tree, so it only runs where /root/reference exists"""
+    if not os.path.exists("/root/reference/bch/main.c"):
+        pytest.skip("reference tree not present on this machine")
+    subprocess.run(["make", "-C", ROOT, "demos"], check=True, stdout=subprocess.DEVNULL)
+    for argv in (["8191", "16", "16"], ["65535", "100", "100"], ["8191", "200", "200"]):
+        out = subprocess.run([os.path.join(ROOT, "host", "bchdemo")] + argv, capture_output=True, text=True)
+        assert out.returncode == 0 and "Test successful" in out.stdout, out.stdout[-500:]
