@@ -14,7 +14,7 @@ struct bchfft_code {
   uint32_t chunk_pos = 0, nchunks = 0, nsub_total = 0;
   uint32_t *d_taps = nullptr, *d_fold = nullptr;
   bchfft::DeviceBuffer scratch, stage_words, stage_ok, stage_corr, stage_a, stage_b, stage_c;
-  bool attr_set = false;
+  size_t smem_set[2] = {0, 0};
 };
 
 namespace bchfft {
@@ -104,16 +104,17 @@ static const int kNtBig = 32;
 static const int kNtBig = 512;
 #endif
 
-// opt in to the large dynamic shared-memory carve-out (per device context)
+// opt in to a large dynamic shared-memory carve-out (per device context); the limit counts the
+// kernels' few bytes of static shared memory too, so ask for what the launch needs
 template <int M>
-static int ensure_attrs(bchfft_code *c)
+static int ensure_smem(bchfft_code *c, int which, size_t bytes)
 {
-  if (c->attr_set) return BCHFFT_OK;
-  BCHFFT_CUDA_TRY(cudaFuncSetAttribute(k_syndrome<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(227 * 1024)));
-  BCHFFT_CUDA_TRY(cudaFuncSetAttribute(k_locate<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(227 * 1024)));
-  c->attr_set = true;
+  if (bytes <= c->smem_set[which]) return BCHFFT_OK;
+  if (which == 0)
+    BCHFFT_CUDA_TRY(cudaFuncSetAttribute(k_syndrome<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  else
+    BCHFFT_CUDA_TRY(cudaFuncSetAttribute(k_locate<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  c->smem_set[which] = bytes;
   return BCHFFT_OK;
 }
 
@@ -123,7 +124,7 @@ static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, 
 {
   const unsigned ns = (unsigned)((cnt + 31) / 32);
   const size_t smem = sizeof(uint32_t) * ((size_t)c->chunk_pos + c->chunk_pos / kSynSub + (size_t)c->nodd * M);
-  int rc0 = ensure_attrs<M>(c);
+  int rc0 = ensure_smem<M>(c, 0, smem);
   if (rc0) return rc0;
   BCHFFT_RUN(k_syndrome<M>, dim3(c->nchunks, ns), dim3(kNtBig), smem, st,
                 (const uint32_t *)d_words, c->wpc * 2u, c->length, (uint32_t)cnt, c->chunk_pos,
@@ -151,17 +152,17 @@ static int launch_locate(bchfft_code *c, size_t cnt, const Scratch &s, uint32_t 
   const int K = ceil_log2u(tcap + 1u);
   int t = c->f->t_max;
   if (t > M) t = M;
-  while (t > K && sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K)) > (size_t)227 * 1024) t--;
-  if (K > t || K > M || sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K)) > (size_t)227 * 1024) {
+  while (t > K && sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K)) > (size_t)226 * 1024) t--;
+  if (K > t || K > M || sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K)) > (size_t)226 * 1024) {
     set_error("bch locate: error-locator degree bound %u too large for one shared-memory tile", tcap);
     return BCHFFT_ERR_UNSUPPORTED;
   }
-  int rc0 = ensure_attrs<M>(c);
-  if (rc0) return rc0;
   PassDesc fwd, bwd;
   locate_descs(M, K, t, fwd, bwd);
   const unsigned ns = (unsigned)((cnt + 31) / 32);
   const size_t smem = sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K));
+  int rc0 = ensure_smem<M>(c, 1, smem);
+  if (rc0) return rc0;
   BCHFFT_RUN(k_locate<M>, dim3(1u << (M - t), ns), dim3(kNtBig), smem, st,
                 (const uint32_t *)s.elp, (const uint32_t *)s.L, (const int32_t *)s.flag, c->d, tcap,
                 (uint32_t)cnt, c->f->tab, fwd, bwd, (const uint32_t *)c->f->d_log, s.count,

@@ -42,7 +42,7 @@ void prof_after();
 
 // field degrees the kernels are instantiated for
 #ifndef BCHFFT_M_LIST
-#define BCHFFT_M_LIST(X) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20)
+#define BCHFFT_M_LIST(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25)
 #endif
 
 struct DeviceBuffer {

@@ -185,3 +185,39 @@ def test_emu_host_api_additive(emu_libs, port):
     res = f.additive_fft_batch(polys, 1023)
     for b in range(5):
         assert (res[b] == port.additive_fft(10, polys[b], 1023)[0]).all()
+
+
+@pytest.mark.parametrize("m", [8, 9, 10, 12])
+def test_emu_multiplicative_fft_vs_oracle(emu_libs, port, m):
+    """secondary kernel: mixed-radix FFT over the cyclic group, full and truncated"""
+    cabi, host = emu_libs
+    n = 1 << m
+    h = _field(cabi, port, m)
+    rng = np.random.default_rng(50 + m)
+    B = 34
+    polys = rng.integers(0, n, (B, n), dtype=np.uint32)
+    for nc in (n - 1, 0, 1, 2, 5, 15, (n - 1) // 3, (n - 1) // 3 + 1):
+        out = np.zeros((B, n), np.uint32)
+        _lib.check(cabi, cabi.bchfft_multiplicative_fft_host(h, polys.ctypes.data, n, out.ctypes.data, n,
+                                                             nc, B), "mfft")
+        for b in (0, 31, 33):
+            want = port.mult_fft(m, polys[b, : n - 1]) if nc == n - 1 else port.mult_eval(m, polys[b], nc)
+            assert (out[b, : n - 1] == want).all(), (m, nc, b)
+    cabi.bchfft_field_destroy(h)
+    # additive and multiplicative paths agree (the relation fft/test.c:147 checks)
+    f = host.create_binary_finite_field(m)
+    p = polys[0].copy()
+    p[n - 1] = 0
+    mult = p.copy()
+    assert f.multiplicative_FFT(mult) == 0
+    add = f.evaluate_polynomial_additive_FFT(p.copy(), n - 1)
+    assert (mult[: n - 1] == add).all()
+    rc, ev = f.evaluate_polynomial_multiplicative_FFT(p, 7)
+    assert rc == 0 and (ev == port.mult_eval(m, p, 7)).all()
+
+
+def test_emu_multiplicative_fft_unknown_factorisation(emu_libs):
+    _, host = emu_libs
+    f = host.create_binary_finite_field(5)
+    data = np.arange(32, dtype=np.uint32)
+    assert f.multiplicative_FFT(data) == 1          # multiplicative_fft.c:110-114

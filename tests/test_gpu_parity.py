@@ -282,3 +282,53 @@ def test_reference_demo_sources_build_and_pass(gpu_libs):
     for argv in (["8191", "16", "16"], ["65535", "100", "100"], ["8191", "200", "200"]):
         out = subprocess.run([os.path.join(ROOT, "host", "bchdemo")] + argv, capture_output=True, text=True)
         assert out.returncode == 0 and "Test successful" in out.stdout, out.stdout[-500:]
+
+
+@pytest.mark.parametrize("m", [8, 12, 16])
+def test_multiplicative_fft_vs_oracle_and_additive(gpu_libs, port, m):
+    """BASELINE configs[4]: multiplicative FFT (2^16-1 = 3*5*17*257), full and truncated, against
+    the oracle and against the additive path on the same polynomial (fft/test.c:147)"""
+    cabi, host = gpu_libs
+    n = 1 << m
+    h = _field(cabi, port, m)
+    B = 40
+    polys = synth.random_polys(m, B, 0xC5)
+    for nc in (n - 1, 0, 1, 2, 15, 255, (n - 1) // 3):
+        nc = min(nc, n - 1)
+        out = np.zeros((B, n), np.uint32)
+        _lib.check(cabi, cabi.bchfft_multiplicative_fft_host(h, polys.ctypes.data, n, out.ctypes.data, n,
+                                                             nc, B), "mfft")
+        for b in (0, 33):
+            want = port.mult_fft(m, polys[b, : n - 1]) if nc == n - 1 else port.mult_eval(m, polys[b], nc)
+            assert (out[b, : n - 1] == want).all(), (m, nc, b)
+    out = np.zeros((B, n), np.uint32)
+    _lib.check(cabi, cabi.bchfft_multiplicative_fft_host(h, polys.ctypes.data, n, out.ctypes.data, n,
+                                                         n - 1, B), "mfft")
+    add, _ = _fft(cabi, h, polys, n - 1, natural=False)
+    assert (out[:, : n - 1] == add).all()
+    cabi.bchfft_field_destroy(h)
+    for rec in [r for r in GOLDEN["multiplicative"] if r["m"] == m]:
+        f = host.create_binary_finite_field(m)
+        from tests.common import multiplicative_input
+        poly = multiplicative_input(rec)
+        if rec.get("truncated"):
+            rc, got = f.evaluate_polynomial_multiplicative_FFT(poly, rec["num_coeffs"])
+        else:
+            data = poly.copy()
+            rc, got = f.multiplicative_FFT(data), data[: n - 1]
+        assert rc == 0 and f"{fnv64(got):016x}" == rec["fnv"]
+
+
+def test_prebuilt_reference_demos_pass(gpu_libs):
+    """host/fftdemo and host/bchdemo are the reference's own demo SOURCES (fft/test.c,
+    bch/main.c) compiled unchanged against our libraries in the build container (`make demos`);
+    here the binaries just have to run and report success"""
+    fftdemo = os.path.join(ROOT, "host", "fftdemo")
+    bchdemo = os.path.join(ROOT, "host", "bchdemo")
+    if not (os.path.exists(fftdemo) and os.path.exists(bchdemo)):
+        pytest.skip("demo binaries not built (need the reference tree at build time)")
+    for argv in (["8191", "16", "16"], ["65535", "100", "100"], ["65535", "1000", "1000"], ["8191", "200", "200"]):
+        out = subprocess.run([bchdemo] + argv, capture_output=True, text=True)
+        assert out.returncode == 0 and "Test successful" in out.stdout, out.stdout[-500:]
+    out = subprocess.run([fftdemo], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "Test successful!" in out.stdout, out.stdout[-800:]
