@@ -14,7 +14,6 @@ struct bchfft_code {
   uint32_t chunk_pos = 0, nchunks = 0, nsub_total = 0;
   uint32_t *d_taps = nullptr, *d_fold = nullptr;
   bchfft::DeviceBuffer scratch, stage_words, stage_ok, stage_corr, stage_a, stage_b, stage_c;
-  size_t smem_set[2] = {0, 0};
 };
 
 namespace bchfft {
@@ -104,28 +103,13 @@ static const int kNtBig = 32;
 static const int kNtBig = 512;
 #endif
 
-// opt in to a large dynamic shared-memory carve-out (per device context); the limit counts the
-// kernels' few bytes of static shared memory too, so ask for what the launch needs
-template <int M>
-static int ensure_smem(bchfft_code *c, int which, size_t bytes)
-{
-  if (bytes <= c->smem_set[which]) return BCHFFT_OK;
-  if (which == 0)
-    BCHFFT_CUDA_TRY(cudaFuncSetAttribute(k_syndrome<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  else
-    BCHFFT_CUDA_TRY(cudaFuncSetAttribute(k_locate<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  c->smem_set[which] = bytes;
-  return BCHFFT_OK;
-}
-
 template <int M>
 static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, const Scratch &s,
                            cudaStream_t st)
 {
   const unsigned ns = (unsigned)((cnt + 31) / 32);
   const size_t smem = sizeof(uint32_t) * ((size_t)c->chunk_pos + c->chunk_pos / kSynSub + (size_t)c->nodd * M);
-  int rc0 = ensure_smem<M>(c, 0, smem);
-  if (rc0) return rc0;
+  BCHFFT_ENSURE_SMEM(k_syndrome<M>, c->f->device, smem);
   BCHFFT_RUN(k_syndrome<M>, dim3(c->nchunks, ns), dim3(kNtBig), smem, st,
                 (const uint32_t *)d_words, c->wpc * 2u, c->length, (uint32_t)cnt, c->chunk_pos,
                 c->nodd, (const uint32_t *)c->d_taps, (const uint32_t *)c->d_fold, c->nsub_total,
@@ -161,8 +145,7 @@ static int launch_locate(bchfft_code *c, size_t cnt, const Scratch &s, uint32_t 
   locate_descs(M, K, t, fwd, bwd);
   const unsigned ns = (unsigned)((cnt + 31) / 32);
   const size_t smem = sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K));
-  int rc0 = ensure_smem<M>(c, 1, smem);
-  if (rc0) return rc0;
+  BCHFFT_ENSURE_SMEM(k_locate<M>, c->f->device, smem);
   BCHFFT_RUN(k_locate<M>, dim3(1u << (M - t), ns), dim3(kNtBig), smem, st,
                 (const uint32_t *)s.elp, (const uint32_t *)s.L, (const int32_t *)s.flag, c->d, tcap,
                 (uint32_t)cnt, c->f->tab, fwd, bwd, (const uint32_t *)c->f->d_log, s.count,

@@ -40,6 +40,20 @@ void prof_after();
     BCHFFT_CUDA_TRY(cudaGetLastError());                                                   \
   } while (0)
 
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute belongs to the function
+// (per device), not to one of our contexts, so the high-water mark is kept per call site and
+// device and is only ever raised.
+#define BCHFFT_ENSURE_SMEM(kernel, device, bytes)                                          \
+  do {                                                                                     \
+    static size_t hw_[64] = {0};                                                           \
+    const int dv_ = (device) & 63;                                                         \
+    if ((size_t)(bytes) > hw_[dv_]) {                                                      \
+      BCHFFT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)(bytes)));                                 \
+      hw_[dv_] = (size_t)(bytes);                                                          \
+    }                                                                                      \
+  } while (0)
+
 // field degrees the kernels are instantiated for
 #ifndef BCHFFT_M_LIST
 #define BCHFFT_M_LIST(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25)
@@ -68,7 +82,6 @@ struct bchfft_field {
   bchfft::DeviceBuffer ws;               // slab workspace
   bchfft::DeviceBuffer stage_in, stage_out, stage_aux;  // device staging for the _host variants
   size_t chunk_bytes = 0;                // workspace budget per chunk of slabs
-  bool fft_attr_set = false;
   // multiplicative FFT state (lazily built)
   void *mfft = nullptr;
 };

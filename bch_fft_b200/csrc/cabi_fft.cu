@@ -38,11 +38,7 @@ static int fft_run(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride,
   uint32_t *bufF = (uint32_t *)f->ws.p;
   uint32_t *bufB = separate ? bufF + chunk * fwd_words : bufF;
 
-  if (!f->fft_attr_set) {   // per context: the opt-in is a per-device function attribute
-    BCHFFT_CUDA_TRY(cudaFuncSetAttribute(k_gm_pass<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(((size_t)4 * M) << f->t_max)));
-    f->fft_attr_set = true;
-  }
+  BCHFFT_ENSURE_SMEM(k_gm_pass<M>, f->device, ((size_t)4 * M) << f->t_max);
   const int nt_io = 128;
 #ifdef BCHFFT_EMU
   const int nt_pass = 32;
