@@ -260,29 +260,30 @@ k_locate(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin,
     }
     transpose32(x);
 #pragma unroll
-    for (int b = 0; b < M; ++b) F[b * TK + i] = x[b];
+    for (int b = 0; b < M; ++b) F[b * TK + swz(i)] = x[b];
     if (i == 0) s_active = act;
   }
   __syncthreads();
   if (s_active == 0u) return;  // nothing to locate in this slab (uniform across the CTA)
   {
     TileGeom g0 = tile_geom(fwd, 0u);
-    tile_run_ops<M>(F, TK, g0, tab, fwd);
+    tile_run_ops<M>(F, TK, fwd.t, g0, tab, fwd);
   }
   const TileGeom g = tile_geom(bwd, blockIdx.x);
   for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
-    const uint32_t src = g.pos(l) & (TK - 1u);
+    const uint32_t src = swz(g.pos(l) & (TK - 1u)) , sl = swz(l);
 #pragma unroll
-    for (int b = 0; b < M; ++b) S[b * T + l] = F[b * TK + src];
+    for (int b = 0; b < M; ++b) S[b * T + sl] = F[b * TK + src];
   }
   __syncthreads();
-  tile_run_ops<M>(S, T, g, tab, bwd);
+  tile_run_ops<M>(S, T, bwd.t, g, tab, bwd);
   const uint32_t active = s_active;
   const uint32_t order = (1u << M) - 1u;
   for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
     uint32_t nz = 0u;
+    const uint32_t sl = swz(l);
 #pragma unroll
-    for (int b = 0; b < M; ++b) nz |= S[b * T + l];
+    for (int b = 0; b < M; ++b) nz |= S[b * T + sl];
     uint32_t roots = ~nz & active;
     if (!roots) continue;
     const uint32_t k = __brev(g.pos(l)) >> (32 - M);

@@ -50,20 +50,44 @@ __device__ __forceinline__ void bs_reduce(uint32_t (&p)[2 * M - 1])
   }
 }
 
+// Products a[i] * c_j accumulate into p[i+j].  Two instruction mixes per partial product:
+//   "alu": p ^= a & mask_j        one LOP3 on the alu pipe (mask_j = 0 / ~0 from bit j of c)
+//   "fma": p ^= a * bit_j         one IMAD on the fma pipe + XOR; pairs of such XORs fuse into one
+//                                 3-input LOP3, so the alu pipe sees half an op per product
+// The alu and fma pipes issue independently (each one warp instruction per two cycles per
+// SMSP on sm_100), so splitting the M*M partial products between them raises the bound from
+// alu-only throughput.  BCHFFT_ALU_ROWS rows (values of j) use the alu mix, the rest the fma mix.
+#ifndef BCHFFT_ALU_ROWS
+#define BCHFFT_ALU_ROWS 2
+#endif
+
+template <int M>
+__device__ __forceinline__ void bs_accumulate_products(uint32_t (&p)[2 * M - 1], const uint32_t (&a)[M],
+                                                       uint32_t c)
+{
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const uint32_t bit = (c >> j) & 1u;
+    if (j < BCHFFT_ALU_ROWS) {
+      const uint32_t mask = 0u - bit;
+#pragma unroll
+      for (int i = 0; i < M; ++i) p[i + j] ^= a[i] & mask;
+    } else {
+#pragma unroll
+      for (int i = 0; i < M; ++i) p[i + j] ^= a[i] * bit;
+    }
+  }
+}
+
 // a <- a * c, c one field element shared by the 32 items of the slab (every additive-FFT
-// multiplier is such a data-independent constant): M*M AND-XOR (one LOP3 each) + reduction.
+// multiplier is such a data-independent constant): M*M partial products + reduction.
 template <int M>
 __device__ __forceinline__ void bs_mul_scalar(uint32_t (&a)[M], uint32_t c)
 {
   uint32_t p[2 * M - 1];
 #pragma unroll
   for (int k = 0; k < 2 * M - 1; ++k) p[k] = 0u;
-#pragma unroll
-  for (int j = 0; j < M; ++j) {
-    const uint32_t mask = 0u - ((c >> j) & 1u);
-#pragma unroll
-    for (int i = 0; i < M; ++i) p[i + j] ^= a[i] & mask;
-  }
+  bs_accumulate_products<M>(p, a, c);
   bs_reduce<M>(p);
 #pragma unroll
   for (int i = 0; i < M; ++i) a[i] = p[i];
@@ -76,12 +100,7 @@ __device__ __forceinline__ void bs_mad_scalar(uint32_t (&acc)[M], const uint32_t
   uint32_t p[2 * M - 1];
 #pragma unroll
   for (int k = 0; k < 2 * M - 1; ++k) p[k] = (k < M) ? acc[k] : 0u;
-#pragma unroll
-  for (int j = 0; j < M; ++j) {
-    const uint32_t mask = 0u - ((c >> j) & 1u);
-#pragma unroll
-    for (int i = 0; i < M; ++i) p[i + j] ^= a[i] & mask;
-  }
+  bs_accumulate_products<M>(p, a, c);
   bs_reduce<M>(p);
 #pragma unroll
   for (int i = 0; i < M; ++i) acc[i] = p[i];

@@ -158,9 +158,12 @@ static int decode_run(bchfft_code *c, uint64_t *d_words, size_t batch, uint8_t *
                       uint32_t *d_corrected, cudaStream_t st)
 {
   const uint32_t pos_stride = c->t + 1u;
-  // chunk the batch so that the per-codeword intermediates stay L2-resident
+  // Chunk the batch only to bound the scratch (about 5 d + t words per codeword).  The decode is
+  // integer-pipe bound by a wide margin (intermediate traffic is ~1.5 KB per codeword), so L2
+  // residency of the intermediates does not matter, whereas small chunks starve the
+  // one-thread-per-codeword kernels of parallelism.
   const char *env = getenv("BCHFFT_DECODE_CHUNK");
-  size_t chunk = env ? (size_t)atol(env) : ((size_t)48 << 20) / (scratch_per_cw(c, pos_stride, M) + c->wpc * 8);
+  size_t chunk = env ? (size_t)atol(env) : ((size_t)1536 << 20) / scratch_per_cw(c, pos_stride, M);
   chunk = (chunk / 32) * 32;
   if (chunk < 32) chunk = 32;
   if (chunk > batch) chunk = batch;

@@ -235,7 +235,7 @@ extern "C" int bchfft_field_create(int device, uint32_t m, const uint32_t *exp, 
   f->h_exp.assign(exp, exp + n);
   f->h_log.assign(log, log + n);
   const char *env = getenv("BCHFFT_CHUNK_MB");
-  f->chunk_bytes = (size_t)(env ? atoi(env) : 64) << 20;
+  f->chunk_bytes = (size_t)(env ? atoi(env) : 1024) << 20;
 
   GmConstants c = gm_constants((int)m, exp, log);
   std::vector<uint32_t> perm_exp(n), perm_nat(n);

@@ -77,6 +77,61 @@ __device__ __forceinline__ TileGeom tile_geom(const PassDesc &d, uint32_t tile)
   return g;
 }
 
+// Shared-memory tiles are XOR-swizzled: local position l lives at word l ^ ((l >> 5) & 31) of its
+// plane, i.e. bank = l[4:0] ^ l[9:5].  A warp whose lanes differ in five local bits that hit the
+// five bank bits independently (one of {i, i+5} for each i) is conflict-free, whichever bits the
+// threads themselves iterate over.
+__device__ __forceinline__ uint32_t swz(uint32_t l) { return l ^ ((l >> 5) & 31u); }
+
+// Enumeration of the 2^(t-r) work items of a sweep in which every thread owns the 2^r positions
+// spanned by local bits [g0, g0+r).  Item bits 0..4 (the lanes of a warp) go to local bit i, or
+// to i+5 when bit i belongs to the thread-owned group, so that the swizzle spreads them over all
+// 32 banks; the remaining item bits fill the other free bits in ascending order.
+struct SweepMap {
+  uint32_t g5;            // lane bits that are shifted up by 5
+  uint32_t start[4], len[4];
+  uint32_t simple, g0, r;
+  __device__ __forceinline__ uint32_t pos(uint32_t w) const
+  {
+    if (simple) return ((w >> g0) << (g0 + r)) | (w & ((1u << g0) - 1u));
+    const uint32_t lane = w & 31u;
+    uint32_t rest = w >> 5;
+    uint32_t l = (lane & ~g5) | ((lane & g5) << 5);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      l |= (rest & ((1u << len[k]) - 1u)) << start[k];
+      rest >>= len[k];
+    }
+    return l;
+  }
+};
+
+__device__ __forceinline__ SweepMap make_sweep_map(uint32_t t, uint32_t g0, uint32_t r)
+{
+  SweepMap m;
+  m.g0 = g0;
+  m.r = r;
+  m.g5 = 0u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) m.start[k] = m.len[k] = 0u;
+  m.simple = (t < 10u || g0 >= 5u || r == 0u) ? 1u : 0u;
+  if (m.simple) return m;
+  const uint32_t group = ((1u << r) - 1u) << g0;
+  m.g5 = group & 31u;
+  uint32_t free_rest = ((1u << t) - 1u) & ~group & ~(31u & ~m.g5) & ~(m.g5 << 5);
+  int k = 0;
+  while (free_rest && k < 4) {
+    const uint32_t s = (uint32_t)__ffs((int)free_rest) - 1u;
+    uint32_t n = 0;
+    while ((free_rest >> (s + n)) & 1u) n++;
+    m.start[k] = s;
+    m.len[k] = n;
+    free_rest &= ~(((1u << n) - 1u) << s);
+    k++;
+  }
+  return m;
+}
+
 template <int M>
 __device__ __forceinline__ void tile_load(uint32_t *S, uint32_t T, const uint32_t *__restrict__ src,
                                           const TileGeom &g, uint32_t src_mask)
@@ -85,13 +140,14 @@ __device__ __forceinline__ void tile_load(uint32_t *S, uint32_t T, const uint32_
   for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
     const uint32_t p = g.pos(l) & src_mask;
     const uint4 *in = reinterpret_cast<const uint4 *>(src + (size_t)p * PS);
+    const uint32_t sl = swz(l);
 #pragma unroll
     for (int v = 0; v < PS / 4; ++v) {
       const uint4 q = in[v];
-      if (4 * v + 0 < M) S[(4 * v + 0) * T + l] = q.x;
-      if (4 * v + 1 < M) S[(4 * v + 1) * T + l] = q.y;
-      if (4 * v + 2 < M) S[(4 * v + 2) * T + l] = q.z;
-      if (4 * v + 3 < M) S[(4 * v + 3) * T + l] = q.w;
+      if (4 * v + 0 < M) S[(4 * v + 0) * T + sl] = q.x;
+      if (4 * v + 1 < M) S[(4 * v + 1) * T + sl] = q.y;
+      if (4 * v + 2 < M) S[(4 * v + 2) * T + sl] = q.z;
+      if (4 * v + 3 < M) S[(4 * v + 3) * T + sl] = q.w;
     }
   }
 }
@@ -103,13 +159,14 @@ __device__ __forceinline__ void tile_store(const uint32_t *S, uint32_t T, uint32
   constexpr int PS = plane_stride(M);
   for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
     uint4 *out = reinterpret_cast<uint4 *>(dst + (size_t)g.pos(l) * PS);
+    const uint32_t sl = swz(l);
 #pragma unroll
     for (int v = 0; v < PS / 4; ++v) {
       uint4 q;
-      q.x = (4 * v + 0 < M) ? S[(4 * v + 0) * T + l] : 0u;
-      q.y = (4 * v + 1 < M) ? S[(4 * v + 1) * T + l] : 0u;
-      q.z = (4 * v + 2 < M) ? S[(4 * v + 2) * T + l] : 0u;
-      q.w = (4 * v + 3 < M) ? S[(4 * v + 3) * T + l] : 0u;
+      q.x = (4 * v + 0 < M) ? S[(4 * v + 0) * T + sl] : 0u;
+      q.y = (4 * v + 1 < M) ? S[(4 * v + 1) * T + sl] : 0u;
+      q.z = (4 * v + 2 < M) ? S[(4 * v + 2) * T + sl] : 0u;
+      q.w = (4 * v + 3 < M) ? S[(4 * v + 3) * T + sl] : 0u;
       out[v] = q;
     }
   }
@@ -123,68 +180,157 @@ __device__ __forceinline__ void tile_twist(uint32_t *S, uint32_t T, const TileGe
   for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
     const uint32_t c = tw_d[g.pos(l) >> d];
     if (c == 1u) continue;
+    const uint32_t sl = swz(l);
     uint32_t a[M];
 #pragma unroll
-    for (int b = 0; b < M; ++b) a[b] = S[b * T + l];
+    for (int b = 0; b < M; ++b) a[b] = S[b * T + sl];
     bs_mul_scalar<M>(a, c);
 #pragma unroll
-    for (int b = 0; b < M; ++b) S[b * T + l] = a[b];
+    for (int b = 0; b < M; ++b) S[b * T + sl] = a[b];
   }
 }
 
-// TY(d, lo): one Taylor-expansion level at x^2+x on position bits (lo+1, lo): Q2 ^= Q3; Q1 ^= Q2
-template <int M>
-__device__ __forceinline__ void tile_taylor(uint32_t *S, uint32_t T, uint32_t lbl)
+// R-1 consecutive Taylor-expansion levels (at x^2+x) on local bits [g0, g0+R): the level on
+// bit pair (lv+1, lv), lv = R-2 .. 0, does Q2 ^= Q3 then Q1 ^= Q2.  XOR only and plane-wise, so
+// a work item is (plane, block of 2^R positions) held in registers.
+template <int M, int R>
+__device__ __forceinline__ void tile_taylor_multi(uint32_t *S, uint32_t T, uint32_t t, uint32_t g0)
 {
-  const uint32_t groups = T >> 2, o1 = 1u << lbl, o2 = 2u << lbl;
-  const uint32_t low_mask = o1 - 1u;
-  for (uint32_t idx = threadIdx.x; idx < groups * M; idx += blockDim.x) {
-    const uint32_t plane = idx / groups, gi = idx - plane * groups;
-    const uint32_t base = ((gi & ~low_mask) << 2) | (gi & low_mask);
-    uint32_t *row = S + plane * T + base;
-    const uint32_t x3 = row[o2 + o1];
-    const uint32_t x2 = row[o2] ^ x3;
-    row[o2] = x2;
-    row[o1] ^= x2;
+  const SweepMap map = make_sweep_map(t, g0, R);
+  const uint32_t blocks = T >> R;
+  for (uint32_t idx = threadIdx.x; idx < blocks * M; idx += blockDim.x) {
+    const uint32_t plane = idx / blocks, w = idx - plane * blocks;
+    const uint32_t base = map.pos(w);
+    uint32_t *row = S + plane * T;
+    uint32_t x[1 << R];
+#pragma unroll
+    for (int k = 0; k < (1 << R); ++k) x[k] = row[swz(base + ((uint32_t)k << g0))];
+#pragma unroll
+    for (int lv = R - 2; lv >= 0; --lv) {
+#pragma unroll
+      for (int k = 0; k < (1 << R); ++k)
+        if (((k >> lv) & 3) == 2) x[k] ^= x[k + (1 << lv)];
+#pragma unroll
+      for (int k = 0; k < (1 << R); ++k)
+        if (((k >> lv) & 3) == 1) x[k] ^= x[k + (1 << lv)];
+    }
+#pragma unroll
+    for (int k = 0; k < (1 << R); ++k) row[swz(base + ((uint32_t)k << g0))] = x[k];
   }
 }
 
 // BF(d): lo' = lo + gam[d][p >> (d+1)] * hi ; hi' = lo' + hi
 template <int M>
-__device__ __forceinline__ void tile_butterfly(uint32_t *S, uint32_t T, const TileGeom &g,
+__device__ __forceinline__ void tile_butterfly(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
                                                const uint32_t *__restrict__ gam_d, uint32_t d, uint32_t lbd)
 {
-  const uint32_t o = 1u << lbd, low_mask = o - 1u;
+  const SweepMap map = make_sweep_map(t, lbd, 1);
+  const uint32_t o = 1u << lbd;
   for (uint32_t j = threadIdx.x; j < (T >> 1); j += blockDim.x) {
-    const uint32_t l = ((j & ~low_mask) << 1) | (j & low_mask);
+    const uint32_t l = map.pos(j);
     const uint32_t G = gam_d[g.pos(l) >> (d + 1)];
+    const uint32_t s0 = swz(l), s1 = swz(l + o);
     uint32_t lo[M], hi[M];
 #pragma unroll
     for (int b = 0; b < M; ++b) {
-      lo[b] = S[b * T + l];
-      hi[b] = S[b * T + l + o];
+      lo[b] = S[b * T + s0];
+      hi[b] = S[b * T + s1];
     }
     if (G) bs_mad_scalar<M>(lo, hi, G);
 #pragma unroll
     for (int b = 0; b < M; ++b) {
-      S[b * T + l] = lo[b];
-      S[b * T + l + o] = lo[b] ^ hi[b];
+      S[b * T + s0] = lo[b];
+      S[b * T + s1] = lo[b] ^ hi[b];
     }
   }
 }
 
+// BF(d) then BF(d-1) on four positions held in registers (local bits lb, lb+1 = bits d-1, d)
 template <int M>
-__device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, const TileGeom &g,
+__device__ __forceinline__ void tile_butterfly_r4(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
+                                                  const uint32_t *__restrict__ gam_d,
+                                                  const uint32_t *__restrict__ gam_dm1, uint32_t d,
+                                                  uint32_t lb)
+{
+  const SweepMap map = make_sweep_map(t, lb, 2);
+  for (uint32_t j = threadIdx.x; j < (T >> 2); j += blockDim.x) {
+    const uint32_t l = map.pos(j);
+    const uint32_t p0 = g.pos(l);
+    const uint32_t s0 = swz(l), s1 = swz(l + (1u << lb)), s2 = swz(l + (2u << lb)), s3 = swz(l + (3u << lb));
+    uint32_t e0[M], e1[M], e2[M], e3[M];
+#pragma unroll
+    for (int b = 0; b < M; ++b) {
+      e0[b] = S[b * T + s0];
+      e1[b] = S[b * T + s1];
+      e2[b] = S[b * T + s2];
+      e3[b] = S[b * T + s3];
+    }
+    const uint32_t G = gam_d[p0 >> (d + 1)];
+    if (G) {
+      bs_mad_scalar<M>(e0, e2, G);
+      bs_mad_scalar<M>(e1, e3, G);
+    }
+#pragma unroll
+    for (int b = 0; b < M; ++b) {
+      e2[b] ^= e0[b];
+      e3[b] ^= e1[b];
+    }
+    const uint32_t Ga = gam_dm1[p0 >> d], Gb = gam_dm1[(p0 >> d) + 1u];
+    if (Ga) bs_mad_scalar<M>(e0, e1, Ga);
+    if (Gb) bs_mad_scalar<M>(e2, e3, Gb);
+#pragma unroll
+    for (int b = 0; b < M; ++b) {
+      S[b * T + s0] = e0[b];
+      S[b * T + s1] = e0[b] ^ e1[b];
+      S[b * T + s2] = e2[b];
+      S[b * T + s3] = e2[b] ^ e3[b];
+    }
+  }
+}
+
+// Runs the ops of a pass on a tile.  Consecutive Taylor levels of one depth on adjacent bits are
+// fused four at a time, consecutive butterfly levels two at a time (register-resident radix
+// blocks): fewer shared-memory round trips and barriers than one sweep per level.
+template <int M>
+__device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
                                              const FftTables &tab, const PassDesc &desc)
 {
-  for (uint32_t i = 0; i < desc.nops; ++i) {
+  uint32_t i = 0;
+  while (i < desc.nops) {
     const PassOp op = desc.ops[i];
     if (op.type == OP_TW) {
       tile_twist<M>(S, T, g, tab.tw + tab.tw_off[op.d], op.d);
+      i += 1;
     } else if (op.type == OP_TY) {
-      tile_taylor<M>(S, T, g.local_bit(op.lo));
+      // ops i .. i+c-1: same depth, lo and local bit both descending by one
+      uint32_t c = 1;
+      while (c < 4 && i + c < desc.nops) {
+        const PassOp nx = desc.ops[i + c];
+        if (nx.type != OP_TY || nx.d != op.d || nx.lo + c != op.lo ||
+            g.local_bit(nx.lo) + c != g.local_bit(op.lo) || g.local_bit(nx.lo + 1u) != g.local_bit(nx.lo) + 1u)
+          break;
+        c++;
+      }
+      const uint32_t g0 = g.local_bit(op.lo) + 1u - c;   // local bit of the last level's lo
+      if (c == 4) tile_taylor_multi<M, 5>(S, T, t, g0);
+      else if (c == 3) tile_taylor_multi<M, 4>(S, T, t, g0);
+      else if (c == 2) tile_taylor_multi<M, 3>(S, T, t, g0);
+      else tile_taylor_multi<M, 2>(S, T, t, g0);
+      i += c;
     } else {
-      tile_butterfly<M>(S, T, g, tab.gam + tab.gam_off[op.d], op.d, g.local_bit(op.d));
+      bool pair = false;
+      if (M <= 16 && i + 1 < desc.nops) {
+        const PassOp nx = desc.ops[i + 1];
+        pair = nx.type == OP_BF && nx.d + 1u == op.d && g.local_bit(nx.d) + 1u == g.local_bit(op.d);
+      }
+      if (pair) {
+        tile_butterfly_r4<M>(S, T, t, g, tab.gam + tab.gam_off[op.d], tab.gam + tab.gam_off[op.d - 1u],
+                             op.d, g.local_bit(op.d) - 1u);
+        i += 2;
+      } else {
+        tile_butterfly<M>(S, T, t, g, tab.gam + tab.gam_off[op.d], op.d, g.local_bit(op.d));
+        i += 1;
+      }
     }
     __syncthreads();
   }
@@ -202,7 +348,7 @@ k_gm_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t s
   const TileGeom g = tile_geom(desc, blockIdx.x);
   tile_load<M>(S, T, src + (size_t)blockIdx.y * src_slab_words, g, desc.src_mask);
   __syncthreads();
-  tile_run_ops<M>(S, T, g, tab, desc);
+  tile_run_ops<M>(S, T, desc.t, g, tab, desc);
   tile_store<M>(S, T, dst + (size_t)blockIdx.y * dst_slab_words, g);
 }
 

@@ -1,0 +1,15 @@
+#!/bin/bash
+# quick GPU check used during kernel iteration: core parity tests + a short bench
+tag=${1:-quick}
+shift
+timeout 900 python -m pytest tests -m gpu -q -x -k "vs_oracle or golden" > gpurun_out/pytest_$tag.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$tag.log
+tail -3 gpurun_out/pytest_$tag.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_$tag.json"))
+print("decode cw/s %.3e  ms %.2f  e2e %.3e" % (d["value"], d["ms_per_step"], (d["e2e"] or {}).get("value",0)))
+print(" shares", d["roofline"]["kernel_share_of_step"])
+f=d["fft"]
+if f: print("fft pts/s %.3e ms %.2f e2e %.3e" % (f["value"], f["ms_per_step"], (f["e2e"] or {}).get("value",0)), f["roofline"]["kernel_share_of_step"])
+PY
