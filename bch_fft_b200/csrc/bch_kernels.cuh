@@ -26,7 +26,7 @@ constexpr int kSynSub = 256;  // positions per LFSR work item
 // parity: [slab] plane word = XOR of all codeword bits (c(1), the reference's FFT-path
 // syndrome[0]).
 template <int M>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(BCHFFT_NT_SYN, BCHFFT_MINB_SYN)
 k_syndrome(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32_t length_bits,
            uint32_t batch, uint32_t chunk_pos, uint32_t nodd, const uint32_t *__restrict__ taps,
            const uint32_t *__restrict__ fold, uint32_t nsub_total, uint32_t *__restrict__ acc,
@@ -219,30 +219,33 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, const int32_t *__restrict
 }
 
 // ---- root search ----------------------------------------------------------------------------
-// Evaluates the error locator of every codeword of a slab at all 2^M field points with the
-// truncated additive FFT: forward phase on the 2^K coefficients (K = ceil(log2(t+1)), tiny,
-// recomputed by every tile), values broadcast over the cosets, K butterfly levels on the tile.
+// The error locator of every codeword is evaluated at all 2^M field points with the truncated
+// additive FFT (the device counterpart of bch.c:406-490's FFT path, with the reference's
+// low-degree shortcut of additive_fft.c:103-110 taken to its conclusion):
+//   k_elp_fwd   bitslice the locator coefficients of 2^sb slabs per CTA and run the forward
+//               phase (twists + Taylor expansions) on the 2^K coefficients, K = ceil(log2(t+1))
+//   k_locate    per tile of 2^t positions: broadcast the 2^K forward values over the cosets,
+//               K butterfly levels, zero test fused into the last level
 // A zero at position p = bitrev_M(k), k = x^i != 0, is an error at bit `order - i`
 // (bch.c:479-488, including the bit-0 quirk: i = 0 reports position `order`).
-// grid = (tiles per slab, slabs); dynamic smem = M * (2^t + 2^K) words.
+
+// grid = ceil(nslabs / 2^sb); dynamic smem = M * 2^(K+sb) words.
+// Fout: [slab][2^K][PS]; active[slab] = mask of codewords that take part (flagged and L <= tcap).
 template <int M>
-__global__ void __launch_bounds__(512, 1)
-k_locate(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin,
-         const int32_t *__restrict__ flag, uint32_t d, uint32_t tcap, uint32_t batch, FftTables tab,
-         PassDesc fwd, PassDesc bwd, const uint32_t *__restrict__ glog, uint32_t *__restrict__ count,
-         uint32_t *__restrict__ positions, uint32_t pos_stride)
+__global__ void __launch_bounds__(256)
+k_elp_fwd(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin,
+          const int32_t *__restrict__ flag, uint32_t d, uint32_t tcap, uint32_t batch, uint32_t nslabs,
+          uint32_t sb, FftTables tab, PassDesc fwd, uint32_t *__restrict__ Fout,
+          uint32_t *__restrict__ active)
 {
-  BCHFFT_DYN_SMEM(uint32_t, smem);
-  const uint32_t K = fwd.dom_bits, TK = 1u << K, T = 1u << bwd.t;
-  uint32_t *S = smem;           // [M][T]
-  uint32_t *F = smem + M * T;   // [M][TK]
-  const uint32_t slab = blockIdx.y;
-  __shared__ uint32_t s_active;
-  if (threadIdx.x == 0) s_active = 0u;
-  __syncthreads();
-  // bitslice the coefficients: coefficient index i of the 32 codewords -> M plane words.
-  // Coefficients above L are not part of the polynomial (bch.c:444-445, 466).
-  for (uint32_t i = threadIdx.x; i < TK; i += blockDim.x) {
+  constexpr int PS = plane_stride(M);
+  BCHFFT_DYN_SMEM(uint32_t, S);
+  const uint32_t K = fwd.dom_bits, TK = 1u << K, tt = K + sb, T = 1u << tt;
+  const uint32_t slab0 = blockIdx.x << sb;
+  // coefficient index i of the 32 codewords of a slab -> M plane words.  Coefficients above L
+  // are not part of the polynomial (bch.c:444-445, 466).
+  for (uint32_t idx = threadIdx.x; idx < T; idx += blockDim.x) {
+    const uint32_t slab = slab0 + (idx >> K), i = idx & (TK - 1u);
     uint32_t x[32];
     uint32_t act = 0u;
 #pragma unroll
@@ -259,36 +262,54 @@ k_locate(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin,
       x[l] = v;
     }
     transpose32(x);
+    const uint32_t sl = swz(idx);
 #pragma unroll
-    for (int b = 0; b < M; ++b) F[b * TK + swz(i)] = x[b];
-    if (i == 0) s_active = act;
+    for (int b = 0; b < M; ++b) S[b * T + sl] = x[b];
+    if (i == 0 && slab < nslabs) active[slab] = act;
   }
   __syncthreads();
-  if (s_active == 0u) return;  // nothing to locate in this slab (uniform across the CTA)
+  TileGeom g;
+  g.fixed = 0u;
+  g.a0 = 0u;
+  g.n0 = tt;
+  g.a1 = tt;
+  g.mask0 = T - 1u;
+  g.pmask = TK - 1u;        // constants depend on the coefficient index only, not on the slab
+  tile_run_ops<M>(S, T, tt, g, tab, fwd);
+  for (uint32_t idx = threadIdx.x; idx < T; idx += blockDim.x) {
+    const uint32_t slab = slab0 + (idx >> K), i = idx & (TK - 1u);
+    if (slab >= nslabs) continue;
+    uint4 *out = reinterpret_cast<uint4 *>(Fout + ((size_t)slab * TK + i) * PS);
+    const uint32_t sl = swz(idx);
+#pragma unroll
+    for (int v = 0; v < PS / 4; ++v) {
+      uint4 q;
+      q.x = (4 * v + 0 < M) ? S[(4 * v + 0) * T + sl] : 0u;
+      q.y = (4 * v + 1 < M) ? S[(4 * v + 1) * T + sl] : 0u;
+      q.z = (4 * v + 2 < M) ? S[(4 * v + 2) * T + sl] : 0u;
+      q.w = (4 * v + 3 < M) ? S[(4 * v + 3) * T + sl] : 0u;
+      out[v] = q;
+    }
+  }
+}
+
+// zero test + root compaction on the final values of a tile
+template <int M>
+struct RootEpilogue {
+  const TileGeom *g;
+  const uint32_t *glog;
+  uint32_t *count, *positions;
+  uint32_t active, slab, pos_stride;
+  __device__ __forceinline__ void operator()(uint32_t l, const uint32_t *v) const
   {
-    TileGeom g0 = tile_geom(fwd, 0u);
-    tile_run_ops<M>(F, TK, fwd.t, g0, tab, fwd);
-  }
-  const TileGeom g = tile_geom(bwd, blockIdx.x);
-  for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
-    const uint32_t src = swz(g.pos(l) & (TK - 1u)) , sl = swz(l);
-#pragma unroll
-    for (int b = 0; b < M; ++b) S[b * T + sl] = F[b * TK + src];
-  }
-  __syncthreads();
-  tile_run_ops<M>(S, T, bwd.t, g, tab, bwd);
-  const uint32_t active = s_active;
-  const uint32_t order = (1u << M) - 1u;
-  for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
     uint32_t nz = 0u;
-    const uint32_t sl = swz(l);
 #pragma unroll
-    for (int b = 0; b < M; ++b) nz |= S[b * T + sl];
+    for (int b = 0; b < M; ++b) nz |= v[b];
     uint32_t roots = ~nz & active;
-    if (!roots) continue;
-    const uint32_t k = __brev(g.pos(l)) >> (32 - M);
-    if (k == 0u) continue;  // P(0) = C[0] = 1 for every active codeword; x^i never reaches 0
-    const uint32_t where = order - glog[k];
+    if (!roots) return;
+    const uint32_t k = __brev(g->pos(l)) >> (32 - M);
+    if (k == 0u) return;   // P(0) = C[0] = 1 for every active codeword; x^i never reaches 0
+    const uint32_t where = ((1u << M) - 1u) - glog[k];
     while (roots) {
       const uint32_t lane = (uint32_t)__ffs((int)roots) - 1u;
       roots &= roots - 1u;
@@ -297,6 +318,33 @@ k_locate(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin,
       if (idx < pos_stride) positions[(size_t)cw * pos_stride + idx] = where;
     }
   }
+};
+
+// grid = (tiles per slab, slabs); dynamic smem = M * 2^t words.
+template <int M>
+__global__ void __launch_bounds__(BCHFFT_NT_LOC, BCHFFT_MINB_LOC)
+k_locate(const uint32_t *__restrict__ F, const uint32_t *__restrict__ active_in, FftTables tab,
+         PassDesc bwd, uint32_t K, const uint32_t *__restrict__ glog, uint32_t *__restrict__ count,
+         uint32_t *__restrict__ positions, uint32_t pos_stride)
+{
+  constexpr int PS = plane_stride(M);
+  BCHFFT_DYN_SMEM(uint32_t, S);
+  const uint32_t TK = 1u << K, T = 1u << bwd.t;
+  const uint32_t slab = blockIdx.y;
+  const uint32_t active = active_in[slab];
+  if (active == 0u) return;   // nothing to locate in this slab (uniform across the CTA)
+  const TileGeom g = tile_geom(bwd, blockIdx.x);
+  tile_load<M>(S, T, F + (size_t)slab * TK * PS, g, TK - 1u);
+  __syncthreads();
+  RootEpilogue<M> epi;
+  epi.g = &g;
+  epi.glog = glog;
+  epi.count = count;
+  epi.positions = positions;
+  epi.active = active;
+  epi.slab = slab;
+  epi.pos_stride = pos_stride;
+  tile_run_ops<M, RootEpilogue<M>>(S, T, bwd.t, g, tab, bwd, &epi);
 }
 
 // ---- verdict + correction (bch.c:531-561) ---------------------------------------------------

@@ -19,6 +19,27 @@
   type *name = reinterpret_cast<type *>(bchfft_dyn_smem_raw)
 #endif
 
+// Launch shapes of the shared-memory tile kernels (threads per CTA, minimum resident CTAs per SM
+// the kernel is compiled for -- the latter bounds registers per thread).  Measured on B200:
+//  * k_gm_pass keeps one 128 KB tile per SM, so it wants as many threads as registers allow;
+//  * k_locate / k_syndrome use half-size tiles, two CTAs of 256 threads per SM: while one CTA
+//    sits in a load phase or at a barrier the other one keeps the integer pipe busy.
+#ifndef BCHFFT_NT_PASS
+#define BCHFFT_NT_PASS 512
+#endif
+#ifndef BCHFFT_NT_LOC
+#define BCHFFT_NT_LOC 256
+#endif
+#ifndef BCHFFT_MINB_LOC
+#define BCHFFT_MINB_LOC 2
+#endif
+#ifndef BCHFFT_NT_SYN
+#define BCHFFT_NT_SYN 256
+#endif
+#ifndef BCHFFT_MINB_SYN
+#define BCHFFT_MINB_SYN 2
+#endif
+
 namespace bchfft {
 
 // Reduction polynomials of the reference's field table (libbase/finite_field.c:9-18,32-35),

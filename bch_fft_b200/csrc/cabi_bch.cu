@@ -13,7 +13,12 @@ struct bchfft_code {
   uint32_t syn_fft_rule = 0; // reference would take its FFT syndrome path (bch.c:240-254)
   uint32_t chunk_pos = 0, nchunks = 0, nsub_total = 0;
   uint32_t *d_taps = nullptr, *d_fold = nullptr;
-  bchfft::DeviceBuffer scratch, stage_words, stage_ok, stage_corr, stage_a, stage_b, stage_c;
+  // work sets: [0] serves the device-pointer and stage-level entry points, [1] and [2] are the
+  // two lanes of the pipelined host entry point (copy-in / decode / copy-out overlap)
+  struct WorkSet {
+    bchfft::DeviceBuffer scratch, fwd_buf, words, ok, corr;
+    cudaStream_t stream = nullptr;
+  } work[3];
 };
 
 namespace bchfft {
@@ -98,9 +103,9 @@ static size_t zero_bytes(const bchfft_code *c, size_t cnt, int M)
 }
 
 #ifdef BCHFFT_EMU
-static const int kNtBig = 32;
+static const int kNtSyn = 32, kNtLoc = 32;
 #else
-static const int kNtBig = 512;
+static const int kNtSyn = BCHFFT_NT_SYN, kNtLoc = BCHFFT_NT_LOC;
 #endif
 
 template <int M>
@@ -110,7 +115,7 @@ static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, 
   const unsigned ns = (unsigned)((cnt + 31) / 32);
   const size_t smem = sizeof(uint32_t) * ((size_t)c->chunk_pos + c->chunk_pos / kSynSub + (size_t)c->nodd * M);
   BCHFFT_ENSURE_SMEM(k_syndrome<M>, c->f->device, smem);
-  BCHFFT_RUN(k_syndrome<M>, dim3(c->nchunks, ns), dim3(kNtBig), smem, st,
+  BCHFFT_RUN(k_syndrome<M>, dim3(c->nchunks, ns), dim3(kNtSyn), smem, st,
                 (const uint32_t *)d_words, c->wpc * 2u, c->length, (uint32_t)cnt, c->chunk_pos,
                 c->nodd, (const uint32_t *)c->d_taps, (const uint32_t *)c->d_fold, c->nsub_total,
                 s.acc, s.parity);
@@ -129,32 +134,49 @@ static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t 
   return BCHFFT_OK;
 }
 
-// tcap: largest L that is located (t for bch_decode, d for the stage-level entry point)
+// tcap: largest L that is located (t for bch_decode, the largest requested degree for the
+// stage-level entry point)
 template <int M>
-static int launch_locate(bchfft_code *c, size_t cnt, const Scratch &s, uint32_t tcap, cudaStream_t st)
+static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, const Scratch &s, uint32_t tcap,
+                         cudaStream_t st)
 {
+  constexpr int PS = plane_stride(M);
   const int K = ceil_log2u(tcap + 1u);
-  int t = c->f->t_max;
+  // half of the largest tile that fits an SM, so that two CTAs are resident (BCHFFT_MINB_LOC)
+  int t = c->f->t_max - 1;
+  if (t < K) t = K;
   if (t > M) t = M;
-  while (t > K && sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K)) > (size_t)226 * 1024) t--;
-  if (K > t || K > M || sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K)) > (size_t)226 * 1024) {
+  const char *tenv = getenv("BCHFFT_LOCATE_T");
+  if (tenv && atoi(tenv) >= K && atoi(tenv) <= c->f->t_max && atoi(tenv) <= M) t = atoi(tenv);
+  if (K > t || K > M) {
     set_error("bch locate: error-locator degree bound %u too large for one shared-memory tile", tcap);
     return BCHFFT_ERR_UNSUPPORTED;
   }
   PassDesc fwd, bwd;
   locate_descs(M, K, t, fwd, bwd);
   const unsigned ns = (unsigned)((cnt + 31) / 32);
-  const size_t smem = sizeof(uint32_t) * M * (((size_t)1 << t) + ((size_t)1 << K));
+  int rc = w.fwd_buf.reserve(((size_t)ns << K) * PS * 4 + (size_t)ns * 4 + 64);
+  if (rc) return rc;
+  uint32_t *F = (uint32_t *)w.fwd_buf.p;
+  uint32_t *active = F + ((size_t)ns << K) * PS;
+  // forward phase: 2^sb slabs per CTA so that a CTA has 256 coefficient columns to work on
+  uint32_t sb = 0;
+  while ((1u << (K + sb)) < 256u) sb++;
+  const size_t smem_f = sizeof(uint32_t) * M * ((size_t)1 << (K + sb));
+  BCHFFT_ENSURE_SMEM(k_elp_fwd<M>, c->f->device, smem_f);
+  BCHFFT_RUN(k_elp_fwd<M>, dim3((ns + (1u << sb) - 1u) >> sb), dim3(256), smem_f, st,
+             (const uint32_t *)s.elp, (const uint32_t *)s.L, (const int32_t *)s.flag, c->d, tcap,
+             (uint32_t)cnt, (uint32_t)ns, sb, c->f->tab, fwd, F, active);
+  const size_t smem = sizeof(uint32_t) * M * ((size_t)1 << t);
   BCHFFT_ENSURE_SMEM(k_locate<M>, c->f->device, smem);
-  BCHFFT_RUN(k_locate<M>, dim3(1u << (M - t), ns), dim3(kNtBig), smem, st,
-                (const uint32_t *)s.elp, (const uint32_t *)s.L, (const int32_t *)s.flag, c->d, tcap,
-                (uint32_t)cnt, c->f->tab, fwd, bwd, (const uint32_t *)c->f->d_log, s.count,
-                s.positions, s.pos_stride);
+  BCHFFT_RUN(k_locate<M>, dim3(1u << (M - t), ns), dim3(kNtLoc), smem, st, (const uint32_t *)F,
+             (const uint32_t *)active, c->f->tab, bwd, (uint32_t)K, (const uint32_t *)c->f->d_log,
+             s.count, s.positions, s.pos_stride);
   return BCHFFT_OK;
 }
 
 template <int M>
-static int decode_run(bchfft_code *c, uint64_t *d_words, size_t batch, uint8_t *d_ok,
+static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words, size_t batch, uint8_t *d_ok,
                       uint32_t *d_corrected, cudaStream_t st)
 {
   const uint32_t pos_stride = c->t + 1u;
@@ -168,18 +190,18 @@ static int decode_run(bchfft_code *c, uint64_t *d_words, size_t batch, uint8_t *
   if (chunk < 32) chunk = 32;
   if (chunk > batch) chunk = batch;
   if (chunk > (size_t)65535 * 32) chunk = (size_t)65535 * 32;
-  int rc = c->scratch.reserve(scratch_bytes(c, chunk, pos_stride, M));
+  int rc = w.scratch.reserve(scratch_bytes(c, chunk, pos_stride, M));
   if (rc) return rc;
   for (size_t i0 = 0; i0 < batch; i0 += chunk) {
     const size_t cnt = batch - i0 < chunk ? batch - i0 : chunk;
     Scratch s;
-    carve(c, c->scratch.p, cnt, pos_stride, M, s);
-    BCHFFT_CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, zero_bytes(c, cnt, M), st));
-    uint64_t *w = d_words + i0 * c->wpc;
-    if ((rc = launch_syndrome<M>(c, w, cnt, s, st))) return rc;
+    carve(c, w.scratch.p, cnt, pos_stride, M, s);
+    BCHFFT_CUDA_TRY(cudaMemsetAsync(w.scratch.p, 0, zero_bytes(c, cnt, M), st));
+    uint64_t *wp = d_words + i0 * c->wpc;
+    if ((rc = launch_syndrome<M>(c, wp, cnt, s, st))) return rc;
     if ((rc = launch_bm<M>(c, cnt, s, st))) return rc;
-    if ((rc = launch_locate<M>(c, cnt, s, c->t, st))) return rc;
-    BCHFFT_RUN(k_correct, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, w, c->wpc,
+    if ((rc = launch_locate<M>(c, w, cnt, s, c->t, st))) return rc;
+    BCHFFT_RUN(k_correct, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, wp, c->wpc,
                   (uint32_t)cnt, (const int32_t *)s.flag, (const uint32_t *)s.L, c->t,
                   (const uint32_t *)s.count, (const uint32_t *)s.positions, s.pos_stride,
                   d_ok ? d_ok + i0 : (uint8_t *)nullptr, d_corrected ? d_corrected + i0 : (uint32_t *)nullptr);
@@ -296,13 +318,14 @@ extern "C" void bchfft_code_destroy(bchfft_code *c)
   cudaStreamSynchronize(c->f->stream);
   cudaFree(c->d_taps);
   cudaFree(c->d_fold);
-  c->scratch.release();
-  c->stage_words.release();
-  c->stage_ok.release();
-  c->stage_corr.release();
-  c->stage_a.release();
-  c->stage_b.release();
-  c->stage_c.release();
+  for (auto &w : c->work) {
+    w.scratch.release();
+    w.fwd_buf.release();
+    w.words.release();
+    w.ok.release();
+    w.corr.release();
+    if (w.stream) cudaStreamDestroy(w.stream);
+  }
   delete c;
 }
 
@@ -324,10 +347,50 @@ extern "C" int bchfft_bch_decode_dev(bchfft_code *c, uint64_t *d_words, size_t b
   if (batch == 0) return BCHFFT_OK;
   BCHFFT_CUDA_TRY(cudaSetDevice(c->f->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->f->stream;
-#define X(M) case M: return decode_run<M>(c, d_words, batch, d_ok, d_corrected, st);
+#define X(M) case M: return decode_run<M>(c, c->work[0], d_words, batch, d_ok, d_corrected, st);
   BCHFFT_DISPATCH_M(c->f->m, X)
 #undef X
 }
+
+// Host-pointer entry point: the batch is cut into chunks that travel through two lanes
+// (stream + staging + scratch each), so the host->device copy of chunk i+1 and the device->host
+// copy of chunk i-1 overlap the decode of chunk i.  (Full overlap needs page-locked host memory;
+// with pageable memory the copies are staged by the driver and mostly serialise.)
+namespace bchfft {
+template <int M>
+static int decode_host_run(bchfft_code *c, uint64_t *words, size_t batch, uint8_t *ok, uint32_t *corrected)
+{
+  const size_t cw_bytes = (size_t)c->wpc * 8;
+  const char *env = getenv("BCHFFT_E2E_CHUNK");
+  size_t per = env ? (size_t)atol(env) : ((size_t)64 << 20) / cw_bytes;
+  per = per < 32 ? 32 : (per / 32) * 32;
+  if (per > batch) per = (batch + 31) / 32 * 32;
+  int rc;
+  for (int l = 1; l <= 2; l++) {
+    bchfft_code::WorkSet &w = c->work[l];
+    if (!w.stream) BCHFFT_CUDA_TRY(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    if ((rc = w.words.reserve(per * cw_bytes))) return rc;
+    if ((rc = w.ok.reserve(per))) return rc;
+    if ((rc = w.corr.reserve(per * 4))) return rc;
+  }
+  int lane = 1;
+  for (size_t i0 = 0; i0 < batch; i0 += per, lane = 3 - lane) {
+    const size_t cnt = batch - i0 < per ? batch - i0 : per;
+    bchfft_code::WorkSet &w = c->work[lane];
+    cudaStream_t st = w.stream;
+    uint64_t *dw = (uint64_t *)w.words.p;
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(dw, words + i0 * c->wpc, cnt * cw_bytes, cudaMemcpyHostToDevice, st));
+    if ((rc = decode_run<M>(c, w, dw, cnt, (uint8_t *)w.ok.p, (uint32_t *)w.corr.p, st))) return rc;
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(words + i0 * c->wpc, dw, cnt * cw_bytes, cudaMemcpyDeviceToHost, st));
+    if (ok) BCHFFT_CUDA_TRY(cudaMemcpyAsync(ok + i0, w.ok.p, cnt, cudaMemcpyDeviceToHost, st));
+    if (corrected)
+      BCHFFT_CUDA_TRY(cudaMemcpyAsync(corrected + i0, w.corr.p, cnt * 4, cudaMemcpyDeviceToHost, st));
+  }
+  BCHFFT_CUDA_TRY(cudaStreamSynchronize(c->work[1].stream));
+  BCHFFT_CUDA_TRY(cudaStreamSynchronize(c->work[2].stream));
+  return BCHFFT_OK;
+}
+}  // namespace bchfft
 
 extern "C" int bchfft_bch_decode_host(bchfft_code *c, uint64_t *words, size_t batch, uint8_t *ok,
                                       uint32_t *corrected)
@@ -338,28 +401,9 @@ extern "C" int bchfft_bch_decode_host(bchfft_code *c, uint64_t *words, size_t ba
   }
   if (batch == 0) return BCHFFT_OK;
   BCHFFT_CUDA_TRY(cudaSetDevice(c->f->device));
-  cudaStream_t st = c->f->stream;
-  const size_t cw_bytes = (size_t)c->wpc * 8;
-  size_t per = ((size_t)256 << 20) / cw_bytes;
-  per = per < 32 ? 32 : (per / 32) * 32;
-  if (per > batch) per = batch;
-  int rc;
-  if ((rc = c->stage_words.reserve(per * cw_bytes))) return rc;
-  if ((rc = c->stage_ok.reserve(per))) return rc;
-  if ((rc = c->stage_corr.reserve(per * 4))) return rc;
-  for (size_t i0 = 0; i0 < batch; i0 += per) {
-    const size_t cnt = batch - i0 < per ? batch - i0 : per;
-    uint64_t *dw = (uint64_t *)c->stage_words.p;
-    BCHFFT_CUDA_TRY(cudaMemcpyAsync(dw, words + i0 * c->wpc, cnt * cw_bytes, cudaMemcpyHostToDevice, st));
-    rc = bchfft_bch_decode_dev(c, dw, cnt, (uint8_t *)c->stage_ok.p, (uint32_t *)c->stage_corr.p, st);
-    if (rc) return rc;
-    BCHFFT_CUDA_TRY(cudaMemcpyAsync(words + i0 * c->wpc, dw, cnt * cw_bytes, cudaMemcpyDeviceToHost, st));
-    if (ok) BCHFFT_CUDA_TRY(cudaMemcpyAsync(ok + i0, c->stage_ok.p, cnt, cudaMemcpyDeviceToHost, st));
-    if (corrected)
-      BCHFFT_CUDA_TRY(cudaMemcpyAsync(corrected + i0, c->stage_corr.p, cnt * 4, cudaMemcpyDeviceToHost, st));
-    BCHFFT_CUDA_TRY(cudaStreamSynchronize(st));
-  }
-  return BCHFFT_OK;
+#define X(M) case M: return decode_host_run<M>(c, words, batch, ok, corrected);
+  BCHFFT_DISPATCH_M(c->f->m, X)
+#undef X
 }
 
 // ---- stage-level entry points ---------------------------------------------------------------
@@ -376,16 +420,16 @@ static int syndrome_stage(bchfft_code *c, const uint64_t *words, size_t batch, u
   per = per < 32 ? 32 : (per / 32) * 32;
   if (per > batch) per = batch;
   int rc;
-  if ((rc = c->stage_words.reserve(per * cw_bytes))) return rc;
-  if ((rc = c->scratch.reserve(scratch_bytes(c, per, pos_stride, M)))) return rc;
+  if ((rc = c->work[0].words.reserve(per * cw_bytes))) return rc;
+  if ((rc = c->work[0].scratch.reserve(scratch_bytes(c, per, pos_stride, M)))) return rc;
   for (size_t i0 = 0; i0 < batch; i0 += per) {
     const size_t cnt = batch - i0 < per ? batch - i0 : per;
     Scratch s;
-    carve(c, c->scratch.p, cnt, pos_stride, M, s);
-    BCHFFT_CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, zero_bytes(c, cnt, M), st));
-    BCHFFT_CUDA_TRY(cudaMemcpyAsync(c->stage_words.p, words + i0 * c->wpc, cnt * cw_bytes,
+    carve(c, c->work[0].scratch.p, cnt, pos_stride, M, s);
+    BCHFFT_CUDA_TRY(cudaMemsetAsync(c->work[0].scratch.p, 0, zero_bytes(c, cnt, M), st));
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(c->work[0].words.p, words + i0 * c->wpc, cnt * cw_bytes,
                                     cudaMemcpyHostToDevice, st));
-    if ((rc = launch_syndrome<M>(c, (const uint64_t *)c->stage_words.p, cnt, s, st))) return rc;
+    if ((rc = launch_syndrome<M>(c, (const uint64_t *)c->work[0].words.p, cnt, s, st))) return rc;
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(syndromes + i0 * c->d, s.syn, cnt * c->d * 4, cudaMemcpyDeviceToHost, st));
     if (flags) BCHFFT_CUDA_TRY(cudaMemcpyAsync(flags + i0, s.flag, cnt * 4, cudaMemcpyDeviceToHost, st));
     BCHFFT_CUDA_TRY(cudaStreamSynchronize(st));
@@ -402,13 +446,13 @@ static int elp_stage(bchfft_code *c, const uint32_t *syndromes, size_t batch, ui
   per = per < 32 ? 32 : (per / 32) * 32;
   if (per > batch) per = batch;
   int rc;
-  if ((rc = c->scratch.reserve(scratch_bytes(c, per, pos_stride, M)))) return rc;
+  if ((rc = c->work[0].scratch.reserve(scratch_bytes(c, per, pos_stride, M)))) return rc;
   std::vector<int32_t> ones(per, 1);
   for (size_t i0 = 0; i0 < batch; i0 += per) {
     const size_t cnt = batch - i0 < per ? batch - i0 : per;
     Scratch s;
-    carve(c, c->scratch.p, cnt, pos_stride, M, s);
-    BCHFFT_CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, zero_bytes(c, cnt, M), st));
+    carve(c, c->work[0].scratch.p, cnt, pos_stride, M, s);
+    BCHFFT_CUDA_TRY(cudaMemsetAsync(c->work[0].scratch.p, 0, zero_bytes(c, cnt, M), st));
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.syn, syndromes + i0 * c->d, cnt * c->d * 4, cudaMemcpyHostToDevice, st));
     // bch_compute_elp runs unconditionally when called directly
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.flag, ones.data(), cnt * 4, cudaMemcpyHostToDevice, st));
@@ -430,7 +474,7 @@ static int locate_stage(bchfft_code *c, const uint32_t *elp, const uint32_t *L, 
   per = per < 32 ? 32 : (per / 32) * 32;
   if (per > batch) per = batch;
   int rc;
-  if ((rc = c->scratch.reserve(scratch_bytes(c, per, pos_stride, M)))) return rc;
+  if ((rc = c->work[0].scratch.reserve(scratch_bytes(c, per, pos_stride, M)))) return rc;
   std::vector<int32_t> ones(per, 1);
   // the FFT is sized for the largest degree actually requested (bch.c:406: p_elp_degree)
   uint32_t lmax = 1;
@@ -439,12 +483,12 @@ static int locate_stage(bchfft_code *c, const uint32_t *elp, const uint32_t *L, 
   for (size_t i0 = 0; i0 < batch; i0 += per) {
     const size_t cnt = batch - i0 < per ? batch - i0 : per;
     Scratch s;
-    carve(c, c->scratch.p, cnt, pos_stride, M, s);
-    BCHFFT_CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, zero_bytes(c, cnt, M), st));
+    carve(c, c->work[0].scratch.p, cnt, pos_stride, M, s);
+    BCHFFT_CUDA_TRY(cudaMemsetAsync(c->work[0].scratch.p, 0, zero_bytes(c, cnt, M), st));
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.elp, elp + i0 * (c->d + 1), cnt * (c->d + 1) * 4, cudaMemcpyHostToDevice, st));
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.L, L + i0, cnt * 4, cudaMemcpyHostToDevice, st));
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(s.flag, ones.data(), cnt * 4, cudaMemcpyHostToDevice, st));
-    if ((rc = launch_locate<M>(c, cnt, s, lmax, st))) return rc;
+    if ((rc = launch_locate<M>(c, c->work[0], cnt, s, lmax, st))) return rc;
     BCHFFT_RUN(k_sort_positions, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, s.positions,
                   s.pos_stride, (const uint32_t *)s.count, (uint32_t)cnt);
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(positions + i0 * pos_stride, s.positions, cnt * pos_stride * 4,
@@ -498,3 +542,18 @@ extern "C" int bchfft_bch_locate_host(bchfft_code *c, const uint32_t *elp, const
   BCHFFT_DISPATCH_M(c->f->m, X)
 #undef X
 }
+
+#ifdef BCHFFT_TRACE
+// debug builds only: sweep trace of CTA (0,0) of the kernels in this translation unit
+extern "C" int bchfft_debug_trace_bch(unsigned long long *out, int max_pairs)
+{
+  unsigned int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, bchfft::g_trace_n, sizeof n);
+  if ((int)n > max_pairs) n = max_pairs;
+  cudaMemcpyFromSymbol(out, bchfft::g_trace, sizeof(unsigned long long) * 2 * n);
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(bchfft::g_trace_n, &zero, sizeof zero);
+  return (int)n;
+}
+#endif

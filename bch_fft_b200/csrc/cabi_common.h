@@ -81,6 +81,11 @@ struct bchfft_field {
   std::map<int, bchfft::GmPlan> plans;   // keyed by K
   bchfft::DeviceBuffer ws;               // slab workspace
   bchfft::DeviceBuffer stage_in, stage_out, stage_aux;  // device staging for the _host variants
+  // two lanes of the pipelined additive-FFT host entry point (copy-in / transform / copy-out overlap)
+  struct Lane {
+    bchfft::DeviceBuffer in, out, aux, ws;
+    cudaStream_t stream = nullptr;
+  } lanes[2];
   size_t chunk_bytes = 0;                // workspace budget per chunk of slabs
   // multiplicative FFT state (lazily built)
   void *mfft = nullptr;

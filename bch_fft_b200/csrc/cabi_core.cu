@@ -284,6 +284,13 @@ extern "C" void bchfft_field_destroy(bchfft_field *f)
   f->stage_in.release();
   f->stage_out.release();
   f->stage_aux.release();
+  for (auto &l : f->lanes) {
+    l.in.release();
+    l.out.release();
+    l.aux.release();
+    l.ws.release();
+    if (l.stream) cudaStreamDestroy(l.stream);
+  }
   if (f->stream) cudaStreamDestroy(f->stream);
   delete f;
 }

@@ -11,7 +11,7 @@ static int ceil_log2(uint32_t x)
 }
 
 template <int M>
-static int fft_run(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride, uint32_t *d_results,
+static int fft_run(bchfft_field *f, DeviceBuffer &ws, const uint32_t *d_polys, size_t poly_stride, uint32_t *d_results,
                    size_t result_stride, uint32_t *d_natural, size_t natural_stride,
                    uint32_t num_terms, size_t batch, cudaStream_t stream)
 {
@@ -33,9 +33,9 @@ static int fft_run(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride,
   if (chunk < 1) chunk = 1;
   if (chunk > nslabs) chunk = nslabs;
   if (chunk > 65535) chunk = 65535;                           // gridDim.y limit
-  int rc = f->ws.reserve(chunk * slab_bytes);
+  int rc = ws.reserve(chunk * slab_bytes);
   if (rc) return rc;
-  uint32_t *bufF = (uint32_t *)f->ws.p;
+  uint32_t *bufF = (uint32_t *)ws.p;
   uint32_t *bufB = separate ? bufF + chunk * fwd_words : bufF;
 
   BCHFFT_ENSURE_SMEM(k_gm_pass<M>, f->device, ((size_t)4 * M) << f->t_max);
@@ -43,7 +43,7 @@ static int fft_run(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride,
 #ifdef BCHFFT_EMU
   const int nt_pass = 32;
 #else
-  const int nt_pass = 512;
+  const int nt_pass = BCHFFT_NT_PASS;
 #endif
   for (size_t s0 = 0; s0 < nslabs; s0 += chunk) {
     const size_t cs = (nslabs - s0 < chunk) ? nslabs - s0 : chunk;
@@ -87,7 +87,7 @@ static int fft_run(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride,
 
 using namespace bchfft;
 
-extern "C" int bchfft_additive_fft_dev(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride,
+static int additive_fft_dev_ws(bchfft_field *f, bchfft::DeviceBuffer &ws, const uint32_t *d_polys, size_t poly_stride,
                                        uint32_t *d_results, size_t result_stride, uint32_t *d_natural,
                                        size_t natural_stride, uint32_t num_terms, size_t batch,
                                        void *stream)
@@ -107,7 +107,7 @@ extern "C" int bchfft_additive_fft_dev(bchfft_field *f, const uint32_t *d_polys,
   switch (f->m) {
 #define X(M)                                                                                      \
   case M:                                                                                         \
-    return fft_run<M>(f, d_polys, poly_stride, d_results, result_stride, d_natural, natural_stride, \
+    return fft_run<M>(f, ws, d_polys, poly_stride, d_results, result_stride, d_natural, natural_stride, \
                       num_terms, batch, st);
     BCHFFT_M_LIST(X)
 #undef X
@@ -116,6 +116,20 @@ extern "C" int bchfft_additive_fft_dev(bchfft_field *f, const uint32_t *d_polys,
   return BCHFFT_ERR_UNSUPPORTED;
 }
 
+extern "C" int bchfft_additive_fft_dev(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride,
+                                       uint32_t *d_results, size_t result_stride, uint32_t *d_natural,
+                                       size_t natural_stride, uint32_t num_terms, size_t batch,
+                                       void *stream)
+{
+  if (!f) {
+    set_error("bchfft_additive_fft_dev: null argument");
+    return BCHFFT_ERR_ARG;
+  }
+  return additive_fft_dev_ws(f, f->ws, d_polys, poly_stride, d_results, result_stride, d_natural,
+                             natural_stride, num_terms, batch, stream);
+}
+
+// Host-pointer entry point, pipelined over two lanes like bchfft_bch_decode_host.
 extern "C" int bchfft_additive_fft_host(bchfft_field *f, const uint32_t *polys, size_t poly_stride,
                                         uint32_t *results, size_t result_stride, uint32_t *natural,
                                         size_t natural_stride, uint32_t num_terms, size_t batch)
@@ -127,33 +141,54 @@ extern "C" int bchfft_additive_fft_host(bchfft_field *f, const uint32_t *polys, 
   if (batch == 0) return BCHFFT_OK;
   BCHFFT_CUDA_TRY(cudaSetDevice(f->device));
   const uint32_t n = f->n;
-  // stage in chunks so that device staging stays bounded (256 MiB of input per chunk)
-  size_t per = ((size_t)256 << 20) / (poly_stride * sizeof(uint32_t));
+  const char *env = getenv("BCHFFT_E2E_CHUNK_MB");
+  size_t per = ((size_t)(env ? atoi(env) : 128) << 20) / ((size_t)n * sizeof(uint32_t));
   per = per < 32 ? 32 : (per / 32) * 32;
-  if (per > batch) per = batch;
+  if (per > batch) per = (batch + 31) / 32 * 32;
   int rc;
-  if ((rc = f->stage_in.reserve(per * (size_t)n * 4))) return rc;
-  if (results && (rc = f->stage_out.reserve(per * (size_t)n * 4))) return rc;
-  if (natural && (rc = f->stage_aux.reserve(per * (size_t)n * 4))) return rc;
-  for (size_t i0 = 0; i0 < batch; i0 += per) {
+  for (auto &l : f->lanes) {
+    if (!l.stream) BCHFFT_CUDA_TRY(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    if ((rc = l.in.reserve(per * (size_t)n * 4))) return rc;
+    if (results && (rc = l.out.reserve(per * (size_t)n * 4))) return rc;
+    if (natural && (rc = l.aux.reserve(per * (size_t)n * 4))) return rc;
+  }
+  int lane = 0;
+  for (size_t i0 = 0; i0 < batch; i0 += per, lane ^= 1) {
     const size_t cnt = batch - i0 < per ? batch - i0 : per;
-    uint32_t *d_in = (uint32_t *)f->stage_in.p;
+    bchfft_field::Lane &l = f->lanes[lane];
+    uint32_t *d_in = (uint32_t *)l.in.p;
     BCHFFT_CUDA_TRY(cudaMemcpy2DAsync(d_in, (size_t)n * 4, polys + i0 * poly_stride, poly_stride * 4,
-                                      (size_t)n * 4, cnt, cudaMemcpyHostToDevice, f->stream));
-    uint32_t *d_res = results ? (uint32_t *)f->stage_out.p : nullptr;
-    uint32_t *d_nat = natural ? (uint32_t *)f->stage_aux.p : nullptr;
-    rc = bchfft_additive_fft_dev(f, d_in, n, d_res, n, d_nat, n, num_terms, cnt, f->stream);
+                                      (size_t)n * 4, cnt, cudaMemcpyHostToDevice, l.stream));
+    uint32_t *d_res = results ? (uint32_t *)l.out.p : nullptr;
+    uint32_t *d_nat = natural ? (uint32_t *)l.aux.p : nullptr;
+    rc = additive_fft_dev_ws(f, l.ws, d_in, n, d_res, n, d_nat, n, num_terms, cnt, l.stream);
     if (rc) return rc;
     // the reference never writes entry n-1 of po_result (additive_fft.c:20): copy n-1 per row
     if (results)
       BCHFFT_CUDA_TRY(cudaMemcpy2DAsync(results + i0 * result_stride, result_stride * 4, d_res,
                                         (size_t)n * 4, (size_t)(n - 1) * 4, cnt,
-                                        cudaMemcpyDeviceToHost, f->stream));
+                                        cudaMemcpyDeviceToHost, l.stream));
     if (natural)
       BCHFFT_CUDA_TRY(cudaMemcpy2DAsync(natural + i0 * natural_stride, natural_stride * 4, d_nat,
                                         (size_t)n * 4, (size_t)n * 4, cnt, cudaMemcpyDeviceToHost,
-                                        f->stream));
-    BCHFFT_CUDA_TRY(cudaStreamSynchronize(f->stream));
+                                        l.stream));
   }
+  BCHFFT_CUDA_TRY(cudaStreamSynchronize(f->lanes[0].stream));
+  BCHFFT_CUDA_TRY(cudaStreamSynchronize(f->lanes[1].stream));
   return BCHFFT_OK;
 }
+
+#ifdef BCHFFT_TRACE
+// debug builds only: read and reset the sweep trace of CTA (0,0)
+extern "C" int bchfft_debug_trace(unsigned long long *out, int max_pairs)
+{
+  unsigned int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, bchfft::g_trace_n, sizeof n);
+  if ((int)n > max_pairs) n = max_pairs;
+  cudaMemcpyFromSymbol(out, bchfft::g_trace, sizeof(unsigned long long) * 2 * n);
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(bchfft::g_trace_n, &zero, sizeof zero);
+  return (int)n;
+}
+#endif

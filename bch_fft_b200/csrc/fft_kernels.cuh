@@ -13,6 +13,26 @@ namespace bchfft {
 
 constexpr int kMaxM = 25;
 
+#ifdef BCHFFT_TRACE
+// debug instrumentation: CTA (0,0) records (tag, clock64) pairs at sweep boundaries
+__device__ unsigned long long g_trace[512];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ void trace_mark(unsigned tag)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+    const unsigned k = g_trace_n;
+    if (k < 255) {
+      g_trace[2 * k] = tag;
+      g_trace[2 * k + 1] = clock64();
+      g_trace_n = k + 1;
+    }
+  }
+}
+#define BCHFFT_MARK(tag) trace_mark(tag)
+#else
+#define BCHFFT_MARK(tag) ((void)0)
+#endif
+
 struct FftTables {
   const uint32_t *tw;
   const uint32_t *gam;
@@ -52,10 +72,10 @@ __global__ void k_bitslice_in(const uint32_t *__restrict__ src, size_t item_stri
 
 // ---- tile helpers ---------------------------------------------------------------------------
 struct TileGeom {
-  uint32_t fixed, a0, n0, a1, mask0;
+  uint32_t fixed, a0, n0, a1, mask0, pmask;
   __device__ __forceinline__ uint32_t pos(uint32_t l) const
   {
-    return fixed | ((l & mask0) << a0) | ((l >> n0) << a1);
+    return (fixed | ((l & mask0) << a0) | ((l >> n0) << a1)) & pmask;
   }
   // local bit index of global position bit b (b must be inside the window)
   __device__ __forceinline__ uint32_t local_bit(uint32_t b) const
@@ -71,6 +91,7 @@ __device__ __forceinline__ TileGeom tile_geom(const PassDesc &d, uint32_t tile)
   g.n0 = d.n0;
   g.a1 = d.a1;
   g.mask0 = (1u << d.n0) - 1u;
+  g.pmask = 0xFFFFFFFFu;
   const uint32_t g0 = d.a0, g1 = d.a1 - d.a0 - d.n0;
   g.fixed = (tile & ((1u << g0) - 1u)) | (((tile >> g0) & ((1u << g1) - 1u)) << (d.a0 + d.n0)) |
             ((tile >> (g0 + g1)) << (d.a1 + d.n1));
@@ -219,10 +240,17 @@ __device__ __forceinline__ void tile_taylor_multi(uint32_t *S, uint32_t T, uint3
   }
 }
 
+// Epilogue hook of the last butterfly sweep of a pass: instead of writing the final values back
+// to the tile, hand them to `epi(local position, planes)` (the root search tests them for zero).
+struct NoEpilogue {
+  __device__ __forceinline__ void operator()(uint32_t, const uint32_t *) const {}
+};
+
 // BF(d): lo' = lo + gam[d][p >> (d+1)] * hi ; hi' = lo' + hi
-template <int M>
+template <int M, class Epi>
 __device__ __forceinline__ void tile_butterfly(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
-                                               const uint32_t *__restrict__ gam_d, uint32_t d, uint32_t lbd)
+                                               const uint32_t *__restrict__ gam_d, uint32_t d, uint32_t lbd,
+                                               const Epi *epi)
 {
   const SweepMap map = make_sweep_map(t, lbd, 1);
   const uint32_t o = 1u << lbd;
@@ -238,19 +266,26 @@ __device__ __forceinline__ void tile_butterfly(uint32_t *S, uint32_t T, uint32_t
     }
     if (G) bs_mad_scalar<M>(lo, hi, G);
 #pragma unroll
-    for (int b = 0; b < M; ++b) {
-      S[b * T + s0] = lo[b];
-      S[b * T + s1] = lo[b] ^ hi[b];
+    for (int b = 0; b < M; ++b) hi[b] ^= lo[b];
+    if (epi) {
+      (*epi)(l, lo);
+      (*epi)(l + o, hi);
+    } else {
+#pragma unroll
+      for (int b = 0; b < M; ++b) {
+        S[b * T + s0] = lo[b];
+        S[b * T + s1] = hi[b];
+      }
     }
   }
 }
 
 // BF(d) then BF(d-1) on four positions held in registers (local bits lb, lb+1 = bits d-1, d)
-template <int M>
+template <int M, class Epi>
 __device__ __forceinline__ void tile_butterfly_r4(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
                                                   const uint32_t *__restrict__ gam_d,
                                                   const uint32_t *__restrict__ gam_dm1, uint32_t d,
-                                                  uint32_t lb)
+                                                  uint32_t lb, const Epi *epi)
 {
   const SweepMap map = make_sweep_map(t, lb, 2);
   for (uint32_t j = threadIdx.x; j < (T >> 2); j += blockDim.x) {
@@ -280,10 +315,22 @@ __device__ __forceinline__ void tile_butterfly_r4(uint32_t *S, uint32_t T, uint3
     if (Gb) bs_mad_scalar<M>(e2, e3, Gb);
 #pragma unroll
     for (int b = 0; b < M; ++b) {
-      S[b * T + s0] = e0[b];
-      S[b * T + s1] = e0[b] ^ e1[b];
-      S[b * T + s2] = e2[b];
-      S[b * T + s3] = e2[b] ^ e3[b];
+      e1[b] ^= e0[b];
+      e3[b] ^= e2[b];
+    }
+    if (epi) {
+      (*epi)(l, e0);
+      (*epi)(l + (1u << lb), e1);
+      (*epi)(l + (2u << lb), e2);
+      (*epi)(l + (3u << lb), e3);
+    } else {
+#pragma unroll
+      for (int b = 0; b < M; ++b) {
+        S[b * T + s0] = e0[b];
+        S[b * T + s1] = e1[b];
+        S[b * T + s2] = e2[b];
+        S[b * T + s3] = e3[b];
+      }
     }
   }
 }
@@ -291,13 +338,15 @@ __device__ __forceinline__ void tile_butterfly_r4(uint32_t *S, uint32_t T, uint3
 // Runs the ops of a pass on a tile.  Consecutive Taylor levels of one depth on adjacent bits are
 // fused four at a time, consecutive butterfly levels two at a time (register-resident radix
 // blocks): fewer shared-memory round trips and barriers than one sweep per level.
-template <int M>
+template <int M, class Epi = NoEpilogue>
 __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
-                                             const FftTables &tab, const PassDesc &desc)
+                                             const FftTables &tab, const PassDesc &desc,
+                                             const Epi *epi = nullptr)
 {
   uint32_t i = 0;
   while (i < desc.nops) {
     const PassOp op = desc.ops[i];
+    BCHFFT_MARK(100u + op.type * 100u + op.d);
     if (op.type == OP_TW) {
       tile_twist<M>(S, T, g, tab.tw + tab.tw_off[op.d], op.d);
       i += 1;
@@ -323,12 +372,14 @@ __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t
         const PassOp nx = desc.ops[i + 1];
         pair = nx.type == OP_BF && nx.d + 1u == op.d && g.local_bit(nx.d) + 1u == g.local_bit(op.d);
       }
+      // the epilogue, if any, replaces the write-back of the pass's final sweep
       if (pair) {
-        tile_butterfly_r4<M>(S, T, t, g, tab.gam + tab.gam_off[op.d], tab.gam + tab.gam_off[op.d - 1u],
-                             op.d, g.local_bit(op.d) - 1u);
+        tile_butterfly_r4<M, Epi>(S, T, t, g, tab.gam + tab.gam_off[op.d], tab.gam + tab.gam_off[op.d - 1u],
+                                  op.d, g.local_bit(op.d) - 1u, (i + 2 == desc.nops) ? epi : nullptr);
         i += 2;
       } else {
-        tile_butterfly<M>(S, T, t, g, tab.gam + tab.gam_off[op.d], op.d, g.local_bit(op.d));
+        tile_butterfly<M, Epi>(S, T, t, g, tab.gam + tab.gam_off[op.d], op.d, g.local_bit(op.d),
+                               (i + 1 == desc.nops) ? epi : nullptr);
         i += 1;
       }
     }
@@ -339,17 +390,20 @@ __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t
 // ---- one pass over every tile of every slab -----------------------------------------------
 // grid = (tiles per slab, slabs); dynamic smem = M * 2^t * 4 bytes.
 template <int M>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(BCHFFT_NT_PASS, 1)
 k_gm_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t src_slab_words,
           size_t dst_slab_words, FftTables tab, PassDesc desc)
 {
   BCHFFT_DYN_SMEM(uint32_t, S);
   const uint32_t T = 1u << desc.t;
   const TileGeom g = tile_geom(desc, blockIdx.x);
+  BCHFFT_MARK(1);
   tile_load<M>(S, T, src + (size_t)blockIdx.y * src_slab_words, g, desc.src_mask);
   __syncthreads();
   tile_run_ops<M>(S, T, desc.t, g, tab, desc);
+  BCHFFT_MARK(2);
   tile_store<M>(S, T, dst + (size_t)blockIdx.y * dst_slab_words, g);
+  BCHFFT_MARK(3);
 }
 
 // ---- bitsliced slabs -> AoS u32, through a position permutation ---------------------------

@@ -1,0 +1,100 @@
+// Micro-benchmark (development aid): throughput of the bitsliced constant multiply on one GPU,
+// for several instruction mixes.  Build + run on the GPU box:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I bch_fft_b200/csrc -DBCHFFT_ALU_ROWS=.. \
+//        tools/bench/mulbench.cu -o /tmp/mulbench && /tmp/mulbench
+#include <cstdio>
+#include <cstdint>
+#include "bs_common.cuh"
+using namespace bchfft;
+
+#ifndef MB_M
+#define MB_M 13
+#endif
+#ifndef MB_VARIANT
+#define MB_VARIANT 0
+#endif
+
+template <int M>
+__device__ __forceinline__ void mad_variant(uint32_t (&acc)[M], const uint32_t (&a)[M], uint32_t c)
+{
+#if MB_VARIANT == 0
+  bs_mad_scalar<M>(acc, a, c);
+#elif MB_VARIANT == 1
+  // Horner over the bits of c: acc += c_j * (a * x^j), a*x^j kept reduced (no 2M-1 accumulator)
+  uint32_t t[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) t[i] = a[i];
+  constexpr uint32_t taps = field_poly(M) & ((1u << M) - 1u);
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const uint32_t mask = 0u - ((c >> j) & 1u);
+#pragma unroll
+    for (int i = 0; i < M; ++i) acc[i] ^= t[i] & mask;
+    // t <- t * x
+    const uint32_t top = t[M - 1];
+#pragma unroll
+    for (int i = M - 1; i >= 1; --i) t[i] = t[i - 1] ^ (((taps >> i) & 1u) ? top : 0u);
+    t[0] = top;   // taps bit 0 is always set
+  }
+#elif MB_VARIANT == 2
+  // predicate-select formulation: p ^= (bit ? a : 0) written with a ternary
+  uint32_t p[2 * M - 1];
+#pragma unroll
+  for (int k = 0; k < 2 * M - 1; ++k) p[k] = (k < M) ? acc[k] : 0u;
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const bool on = (c >> j) & 1u;
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i + j] ^= on ? a[i] : 0u;
+  }
+  bs_reduce<M>(p);
+#pragma unroll
+  for (int i = 0; i < M; ++i) acc[i] = p[i];
+#endif
+}
+
+__global__ void __launch_bounds__(512, 1) k(uint32_t *out, const uint32_t *consts, int iters)
+{
+  uint32_t acc[MB_M], a[MB_M];
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < MB_M; ++i) {
+    acc[i] = tid * 2654435761u + i;
+    a[i] = tid * 40503u + 7 * i + 1;
+  }
+  for (int it = 0; it < iters; ++it) {
+    const uint32_t c = consts[(tid + it) & 1023];
+    mad_variant<MB_M>(acc, a, c);
+#pragma unroll
+    for (int i = 0; i < MB_M; ++i) a[i] ^= acc[(i + 1) % MB_M];
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < MB_M; ++i) r ^= acc[i];
+  out[tid] = r;
+}
+
+int main()
+{
+  uint32_t *out, *consts;
+  cudaMalloc(&out, 148 * 512 * 4);
+  cudaMalloc(&consts, 1024 * 4);
+  uint32_t h[1024];
+  for (int i = 0; i < 1024; i++) h[i] = (i * 2654435761u >> 7) & ((1u << MB_M) - 1u);
+  cudaMemcpy(consts, h, sizeof h, cudaMemcpyHostToDevice);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  const int iters = 4000;
+  k<<<148, 512>>>(out, consts, 100);
+  cudaEventRecord(a);
+  k<<<148, 512>>>(out, consts, iters);
+  cudaEventRecord(b);
+  cudaEventSynchronize(b);
+  float ms;
+  cudaEventElapsedTime(&ms, a, b);
+  const double mults = 148.0 * 512 * iters;
+  printf("M=%d variant=%d alu_rows=%d: %.3f ms, %.1f G mult/s, %.1f clk per mult per SMSP-warp (at 1.9 GHz: %.0f)\n",
+         MB_M, MB_VARIANT, BCHFFT_ALU_ROWS, ms, mults / ms / 1e6, 0.0, ms * 1e-3 * 1.9e9 / (iters * 4.0));
+  return 0;
+}

@@ -1,0 +1,15 @@
+#!/bin/bash
+# args: "nvcc flags|env assignments" ...
+for v in "$@"; do
+  flags="${v%%|*}"; envs="${v#*|}"
+  make -C bch_fft_b200/csrc clean > /dev/null
+  make -C bch_fft_b200/csrc -j16 all EXTRA_NVFLAGS="-DBCHFFT_M_LIST\(X\)=X\(13\)X\(16\) $flags" > /dev/null 2> gpurun_out/build_err.log || { echo "build failed for $v"; tail -5 gpurun_out/build_err.log; continue; }
+  env $envs python bench.py --steps 5 --warmup 2 --no-cpu-baseline --no-e2e --fft-batch 2048 > gpurun_out/bench_var.json 2> gpurun_out/bench_var.err || { echo "bench failed for $v"; tail -3 gpurun_out/bench_var.err; continue; }
+  python - "$v" <<'PY'
+import json, sys
+d=json.load(open("gpurun_out/bench_var.json"))
+sh=d["roofline"]["kernel_share_of_step"]; ms=d["ms_per_step"]
+f=d["fft"]
+print("VARIANT [%s]: decode %.2f ms (locate %.2f fwd %.2f syn %.2f bm %.2f) | fft16 %.2f ms | parity-free" % (sys.argv[1], ms, ms*sh.get("k_locate",0), ms*sh.get("k_elp_fwd",0), ms*sh["k_syndrome"], ms*sh["k_bm"], f["ms_per_step"]))
+PY
+done
