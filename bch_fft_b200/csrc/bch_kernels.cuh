@@ -226,7 +226,7 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, const int32_t *__restrict
 //               phase (twists + Taylor expansions) on the 2^K coefficients, K = ceil(log2(t+1))
 //   k_locate    per tile of 2^t positions: broadcast the 2^K forward values over the cosets,
 //               K butterfly levels, zero test fused into the last level
-// A zero at position p = bitrev_M(k), k = x^i != 0, is an error at bit `order - i`
+// A zero at the tile position that holds the field point k = x^i != 0 is an error at bit `order - i`
 // (bch.c:479-488, including the bit-0 quirk: i = 0 reports position `order`).
 
 // grid = ceil(nslabs / 2^sb); dynamic smem = M * 2^(K+sb) words.
@@ -297,7 +297,7 @@ k_elp_fwd(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin,
 template <int M>
 struct RootEpilogue {
   const TileGeom *g;
-  const uint32_t *glog;
+  const uint32_t *errloc;   // tile position -> reported error position (0xFFFFFFFF: the point 0)
   uint32_t *count, *positions;
   uint32_t active, slab, pos_stride;
   __device__ __forceinline__ void operator()(uint32_t l, const uint32_t *v) const
@@ -307,9 +307,8 @@ struct RootEpilogue {
     for (int b = 0; b < M; ++b) nz |= v[b];
     uint32_t roots = ~nz & active;
     if (!roots) return;
-    const uint32_t k = __brev(g->pos(l)) >> (32 - M);
-    if (k == 0u) return;   // P(0) = C[0] = 1 for every active codeword; x^i never reaches 0
-    const uint32_t where = ((1u << M) - 1u) - glog[k];
+    const uint32_t where = errloc[g->pos(l)];
+    if (where == 0xFFFFFFFFu) return;   // P(0) = C[0] = 1 for every active codeword; x^i never reaches 0
     while (roots) {
       const uint32_t lane = (uint32_t)__ffs((int)roots) - 1u;
       roots &= roots - 1u;
@@ -324,7 +323,7 @@ struct RootEpilogue {
 template <int M>
 __global__ void __launch_bounds__(BCHFFT_NT_LOC, BCHFFT_MINB_LOC)
 k_locate(const uint32_t *__restrict__ F, const uint32_t *__restrict__ active_in, FftTables tab,
-         PassDesc bwd, uint32_t K, const uint32_t *__restrict__ glog, uint32_t *__restrict__ count,
+         PassDesc bwd, uint32_t K, const uint32_t *__restrict__ errloc, uint32_t *__restrict__ count,
          uint32_t *__restrict__ positions, uint32_t pos_stride)
 {
   constexpr int PS = plane_stride(M);
@@ -338,7 +337,7 @@ k_locate(const uint32_t *__restrict__ F, const uint32_t *__restrict__ active_in,
   __syncthreads();
   RootEpilogue<M> epi;
   epi.g = &g;
-  epi.glog = glog;
+  epi.errloc = errloc;
   epi.count = count;
   epi.positions = positions;
   epi.active = active;

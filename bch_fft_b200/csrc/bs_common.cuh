@@ -27,6 +27,9 @@
 #ifndef BCHFFT_NT_PASS
 #define BCHFFT_NT_PASS 512
 #endif
+#ifndef BCHFFT_MINB_PASS
+#define BCHFFT_MINB_PASS 1
+#endif
 #ifndef BCHFFT_NT_LOC
 #define BCHFFT_NT_LOC 256
 #endif
@@ -57,17 +60,45 @@ __host__ __device__ constexpr uint32_t field_poly(int m)
 // a whole number of 16-byte vectors
 __host__ __device__ constexpr int plane_stride(int m) { return (m + 3) & ~3; }
 
-// p[0 .. 2M-2] -> p[0 .. M-1] modulo the field polynomial (top-down so that every fold-in lands
-// on a plane that is reduced later or is final)
+// three-input XOR: one LOP3
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c)
+{
+#ifdef BCHFFT_EMU
+  return a ^ b ^ c;
+#else
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#endif
+}
+
+// p[0 .. 2M-2] -> p[0 .. M-1] modulo the field polynomial.  Gather form: plane j receives plane
+// j + M - e for every tap e of the polynomial (x^M = sum_e x^e); going from the top plane down,
+// every source is already final when it is used.  The (at most five) inputs of a plane are
+// folded with three-input XORs: 2 LOP3 per plane for the pentanomials, 1 for the trinomials.
 template <int M>
 __device__ __forceinline__ void bs_reduce(uint32_t (&p)[2 * M - 1])
 {
   constexpr uint32_t taps = field_poly(M) & ((1u << M) - 1u);
 #pragma unroll
-  for (int k = 2 * M - 2; k >= M; --k) {
+  for (int j = 2 * M - 3; j >= 0; --j) {
+    uint32_t acc = p[j], pend = 0u;
+    bool have = false;
 #pragma unroll
-    for (int e = 0; e < M; ++e)
-      if ((taps >> e) & 1u) p[k - M + e] ^= p[k];
+    for (int e = 0; e < M; ++e) {
+      const int k = j + M - e;
+      if (((taps >> e) & 1u) && k >= M && k <= 2 * M - 2) {
+        if (have) {
+          acc = xor3(acc, pend, p[k]);
+          have = false;
+        } else {
+          pend = p[k];
+          have = true;
+        }
+      }
+    }
+    if (have) acc ^= pend;
+    p[j] = acc;
   }
 }
 
@@ -79,7 +110,7 @@ __device__ __forceinline__ void bs_reduce(uint32_t (&p)[2 * M - 1])
 // SMSP on sm_100), so splitting the M*M partial products between them raises the bound from
 // alu-only throughput.  BCHFFT_ALU_ROWS rows (values of j) use the alu mix, the rest the fma mix.
 #ifndef BCHFFT_ALU_ROWS
-#define BCHFFT_ALU_ROWS 2
+#define BCHFFT_ALU_ROWS 32
 #endif
 
 template <int M>
@@ -90,7 +121,8 @@ __device__ __forceinline__ void bs_accumulate_products(uint32_t (&p)[2 * M - 1],
   for (int j = 0; j < M; ++j) {
     const uint32_t bit = (c >> j) & 1u;
     if (j < BCHFFT_ALU_ROWS) {
-      const uint32_t mask = 0u - bit;
+      // 0 / ~0 from bit j: shift it to the sign position, arithmetic shift back
+      const uint32_t mask = (uint32_t)((int32_t)(c << (31 - j)) >> 31);
 #pragma unroll
       for (int i = 0; i < M; ++i) p[i + j] ^= a[i] & mask;
     } else {

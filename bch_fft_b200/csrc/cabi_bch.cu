@@ -13,12 +13,12 @@ struct bchfft_code {
   uint32_t syn_fft_rule = 0; // reference would take its FFT syndrome path (bch.c:240-254)
   uint32_t chunk_pos = 0, nchunks = 0, nsub_total = 0;
   uint32_t *d_taps = nullptr, *d_fold = nullptr;
-  // work sets: [0] serves the device-pointer and stage-level entry points, [1] and [2] are the
-  // two lanes of the pipelined host entry point (copy-in / decode / copy-out overlap)
+  // work sets: [0] serves the device-pointer and stage-level entry points, [1] .. [3] are the
+  // lanes of the pipelined host entry point (copy-in / decode / copy-out overlap)
   struct WorkSet {
     bchfft::DeviceBuffer scratch, fwd_buf, words, ok, corr;
     cudaStream_t stream = nullptr;
-  } work[3];
+  } work[4];
 };
 
 namespace bchfft {
@@ -32,7 +32,7 @@ static int ceil_log2u(uint32_t x)
 
 // forward / backward descriptors of the truncated FFT used for root search: forward on the
 // 2^K coefficients (window [0,K)), backward K butterfly levels on tiles [0,t)
-static void locate_descs(int m, int K, int t, PassDesc &fwd, PassDesc &bwd)
+static void locate_descs(int m, int K, int t, uint32_t twist_free, PassDesc &fwd, PassDesc &bwd)
 {
   memset(&fwd, 0, sizeof fwd);
   memset(&bwd, 0, sizeof bwd);
@@ -44,7 +44,7 @@ static void locate_descs(int m, int K, int t, PassDesc &fwd, PassDesc &bwd)
   fwd.n1 = 0;
   fwd.src_mask = 0xFFFFFFFFu;
   for (int d = 0; d < K; d++) {
-    fwd.ops[fwd.nops++] = PassOp{OP_TW, (uint8_t)d, 0, 0};
+    if (!((twist_free >> d) & 1u)) fwd.ops[fwd.nops++] = PassOp{OP_TW, (uint8_t)d, 0, 0};
     for (int lo = K - 2; lo >= d; lo--) fwd.ops[fwd.nops++] = PassOp{OP_TY, (uint8_t)d, (uint8_t)lo, 0};
   }
   bwd.dom_bits = m;
@@ -153,7 +153,7 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
     return BCHFFT_ERR_UNSUPPORTED;
   }
   PassDesc fwd, bwd;
-  locate_descs(M, K, t, fwd, bwd);
+  locate_descs(M, K, t, c->f->twist_free, fwd, bwd);
   const unsigned ns = (unsigned)((cnt + 31) / 32);
   int rc = w.fwd_buf.reserve(((size_t)ns << K) * PS * 4 + (size_t)ns * 4 + 64);
   if (rc) return rc;
@@ -170,7 +170,7 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
   const size_t smem = sizeof(uint32_t) * M * ((size_t)1 << t);
   BCHFFT_ENSURE_SMEM(k_locate<M>, c->f->device, smem);
   BCHFFT_RUN(k_locate<M>, dim3(1u << (M - t), ns), dim3(kNtLoc), smem, st, (const uint32_t *)F,
-             (const uint32_t *)active, c->f->tab, bwd, (uint32_t)K, (const uint32_t *)c->f->d_log,
+             (const uint32_t *)active, c->f->tab, bwd, (uint32_t)K, (const uint32_t *)c->f->d_errloc,
              s.count, s.positions, s.pos_stride);
   return BCHFFT_OK;
 }
@@ -352,7 +352,7 @@ extern "C" int bchfft_bch_decode_dev(bchfft_code *c, uint64_t *d_words, size_t b
 #undef X
 }
 
-// Host-pointer entry point: the batch is cut into chunks that travel through two lanes
+// Host-pointer entry point: the batch is cut into chunks that travel through up to three lanes
 // (stream + staging + scratch each), so the host->device copy of chunk i+1 and the device->host
 // copy of chunk i-1 overlap the decode of chunk i.  (Full overlap needs page-locked host memory;
 // with pageable memory the copies are staged by the driver and mostly serialise.)
@@ -366,7 +366,9 @@ static int decode_host_run(bchfft_code *c, uint64_t *words, size_t batch, uint8_
   per = per < 32 ? 32 : (per / 32) * 32;
   if (per > batch) per = (batch + 31) / 32 * 32;
   int rc;
-  for (int l = 1; l <= 2; l++) {
+  const char *lenv = getenv("BCHFFT_E2E_LANES");
+  const int nlanes = (lenv && atoi(lenv) >= 1 && atoi(lenv) <= 3) ? atoi(lenv) : 3;
+  for (int l = 1; l <= nlanes; l++) {
     bchfft_code::WorkSet &w = c->work[l];
     if (!w.stream) BCHFFT_CUDA_TRY(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     if ((rc = w.words.reserve(per * cw_bytes))) return rc;
@@ -374,7 +376,7 @@ static int decode_host_run(bchfft_code *c, uint64_t *words, size_t batch, uint8_
     if ((rc = w.corr.reserve(per * 4))) return rc;
   }
   int lane = 1;
-  for (size_t i0 = 0; i0 < batch; i0 += per, lane = 3 - lane) {
+  for (size_t i0 = 0; i0 < batch; i0 += per, lane = lane % nlanes + 1) {
     const size_t cnt = batch - i0 < per ? batch - i0 : per;
     bchfft_code::WorkSet &w = c->work[lane];
     cudaStream_t st = w.stream;
@@ -386,8 +388,7 @@ static int decode_host_run(bchfft_code *c, uint64_t *words, size_t batch, uint8_
     if (corrected)
       BCHFFT_CUDA_TRY(cudaMemcpyAsync(corrected + i0, w.corr.p, cnt * 4, cudaMemcpyDeviceToHost, st));
   }
-  BCHFFT_CUDA_TRY(cudaStreamSynchronize(c->work[1].stream));
-  BCHFFT_CUDA_TRY(cudaStreamSynchronize(c->work[2].stream));
+  for (int l = 1; l <= nlanes; l++) BCHFFT_CUDA_TRY(cudaStreamSynchronize(c->work[l].stream));
   return BCHFFT_OK;
 }
 }  // namespace bchfft

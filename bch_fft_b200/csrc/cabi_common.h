@@ -76,7 +76,8 @@ struct bchfft_field {
   cudaStream_t stream = nullptr;
   std::vector<uint32_t> h_exp, h_log;
   uint32_t *d_tw = nullptr, *d_gam = nullptr, *d_perm_exp = nullptr, *d_perm_nat = nullptr;
-  uint32_t *d_exp = nullptr, *d_log = nullptr;
+  uint32_t *d_exp = nullptr, *d_log = nullptr, *d_errloc = nullptr;
+  uint32_t twist_free = 0;               // depths whose twist is the identity (gm_plan.h)
   bchfft::FftTables tab;
   std::map<int, bchfft::GmPlan> plans;   // keyed by K
   bchfft::DeviceBuffer ws;               // slab workspace

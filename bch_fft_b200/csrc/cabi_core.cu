@@ -238,13 +238,21 @@ extern "C" int bchfft_field_create(int device, uint32_t m, const uint32_t *exp, 
   f->chunk_bytes = (size_t)(env ? atoi(env) : 1024) << 20;
 
   GmConstants c = gm_constants((int)m, exp, log);
-  std::vector<uint32_t> perm_exp(n), perm_nat(n);
-  for (uint32_t k = 0; k < n; k++) perm_nat[k] = bitrev_bits(k, (int)m);
+  // position of every evaluation point: natural order (clobbered p_poly) and exp order (po_result)
+  std::vector<uint32_t> perm_exp(n), perm_nat(c.pos_of_elem), errloc(n);
   for (uint32_t i = 0; i < n - 1u; i++) perm_exp[i] = perm_nat[exp[i]];
   perm_exp[n - 1] = 0;
+  // bch_locate_errors: a root at field element k = x^i is reported as position order - i
+  // (bch.c:479-488); per tile position, 0xFFFFFFFF for the point 0
+  for (uint32_t p = 0; p < n; p++) {
+    const uint32_t k = c.elem_of_pos[p];
+    errloc[p] = k ? (n - 1u) - log[k] : 0xFFFFFFFFu;
+  }
+  f->twist_free = c.twist_free;
   int rc = BCHFFT_OK;
   if ((rc = upload_vec(c.tw, &f->d_tw)) || (rc = upload_vec(c.gam, &f->d_gam)) ||
       (rc = upload_vec(perm_exp, &f->d_perm_exp)) || (rc = upload_vec(perm_nat, &f->d_perm_nat)) ||
+      (rc = upload_vec(errloc, &f->d_errloc)) ||
       (rc = upload_vec(f->h_exp, &f->d_exp)) || (rc = upload_vec(f->h_log, &f->d_log))) {
     bchfft_field_destroy(f);
     return rc;
@@ -278,6 +286,7 @@ extern "C" void bchfft_field_destroy(bchfft_field *f)
   cudaFree(f->d_gam);
   cudaFree(f->d_perm_exp);
   cudaFree(f->d_perm_nat);
+  cudaFree(f->d_errloc);
   cudaFree(f->d_exp);
   cudaFree(f->d_log);
   f->ws.release();

@@ -21,7 +21,7 @@ static int fft_run(bchfft_field *f, DeviceBuffer &ws, const uint32_t *d_polys, s
   const uint32_t ncoef = (num_terms >= n - 1u ? n - 1u : num_terms) + 1u;
   const int K = ceil_log2(ncoef);
   auto it = f->plans.find(K);
-  if (it == f->plans.end()) it = f->plans.emplace(K, gm_plan(M, K, f->t_max)).first;
+  if (it == f->plans.end()) it = f->plans.emplace(K, gm_plan(M, K, f->t_max, f->twist_free)).first;
   const GmPlan &plan = it->second;
 
   const size_t fwd_words = ((size_t)1 << K) * PS;            // per slab

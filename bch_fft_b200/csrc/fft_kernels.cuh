@@ -153,22 +153,38 @@ __device__ __forceinline__ SweepMap make_sweep_map(uint32_t t, uint32_t g0, uint
   return m;
 }
 
+// Global <-> shared tile copies.  Four positions per thread are in flight at once (all vector
+// loads issued before the first use) so that the copy is bandwidth- rather than latency-bound.
 template <int M>
 __device__ __forceinline__ void tile_load(uint32_t *S, uint32_t T, const uint32_t *__restrict__ src,
                                           const TileGeom &g, uint32_t src_mask)
 {
   constexpr int PS = plane_stride(M);
-  for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
-    const uint32_t p = g.pos(l) & src_mask;
-    const uint4 *in = reinterpret_cast<const uint4 *>(src + (size_t)p * PS);
-    const uint32_t sl = swz(l);
+  constexpr int U = 4;
+  for (uint32_t base = threadIdx.x; base < T; base += U * blockDim.x) {
+    uint4 q[U][PS / 4];
 #pragma unroll
-    for (int v = 0; v < PS / 4; ++v) {
-      const uint4 q = in[v];
-      if (4 * v + 0 < M) S[(4 * v + 0) * T + sl] = q.x;
-      if (4 * v + 1 < M) S[(4 * v + 1) * T + sl] = q.y;
-      if (4 * v + 2 < M) S[(4 * v + 2) * T + sl] = q.z;
-      if (4 * v + 3 < M) S[(4 * v + 3) * T + sl] = q.w;
+    for (int u = 0; u < U; ++u) {
+      const uint32_t l = base + u * blockDim.x;
+      if (l < T) {
+        const uint4 *in = reinterpret_cast<const uint4 *>(src + (size_t)(g.pos(l) & src_mask) * PS);
+#pragma unroll
+        for (int v = 0; v < PS / 4; ++v) q[u][v] = in[v];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t l = base + u * blockDim.x;
+      if (l < T) {
+        const uint32_t sl = swz(l);
+#pragma unroll
+        for (int v = 0; v < PS / 4; ++v) {
+          if (4 * v + 0 < M) S[(4 * v + 0) * T + sl] = q[u][v].x;
+          if (4 * v + 1 < M) S[(4 * v + 1) * T + sl] = q[u][v].y;
+          if (4 * v + 2 < M) S[(4 * v + 2) * T + sl] = q[u][v].z;
+          if (4 * v + 3 < M) S[(4 * v + 3) * T + sl] = q[u][v].w;
+        }
+      }
     }
   }
 }
@@ -178,17 +194,31 @@ __device__ __forceinline__ void tile_store(const uint32_t *S, uint32_t T, uint32
                                            const TileGeom &g)
 {
   constexpr int PS = plane_stride(M);
-  for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
-    uint4 *out = reinterpret_cast<uint4 *>(dst + (size_t)g.pos(l) * PS);
-    const uint32_t sl = swz(l);
+  constexpr int U = 2;
+  for (uint32_t base = threadIdx.x; base < T; base += U * blockDim.x) {
+    uint4 q[U][PS / 4];
 #pragma unroll
-    for (int v = 0; v < PS / 4; ++v) {
-      uint4 q;
-      q.x = (4 * v + 0 < M) ? S[(4 * v + 0) * T + sl] : 0u;
-      q.y = (4 * v + 1 < M) ? S[(4 * v + 1) * T + sl] : 0u;
-      q.z = (4 * v + 2 < M) ? S[(4 * v + 2) * T + sl] : 0u;
-      q.w = (4 * v + 3 < M) ? S[(4 * v + 3) * T + sl] : 0u;
-      out[v] = q;
+    for (int u = 0; u < U; ++u) {
+      const uint32_t l = base + u * blockDim.x;
+      if (l < T) {
+        const uint32_t sl = swz(l);
+#pragma unroll
+        for (int v = 0; v < PS / 4; ++v) {
+          q[u][v].x = (4 * v + 0 < M) ? S[(4 * v + 0) * T + sl] : 0u;
+          q[u][v].y = (4 * v + 1 < M) ? S[(4 * v + 1) * T + sl] : 0u;
+          q[u][v].z = (4 * v + 2 < M) ? S[(4 * v + 2) * T + sl] : 0u;
+          q[u][v].w = (4 * v + 3 < M) ? S[(4 * v + 3) * T + sl] : 0u;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t l = base + u * blockDim.x;
+      if (l < T) {
+        uint4 *out = reinterpret_cast<uint4 *>(dst + (size_t)g.pos(l) * PS);
+#pragma unroll
+        for (int v = 0; v < PS / 4; ++v) out[v] = q[u][v];
+      }
     }
   }
 }
@@ -198,16 +228,25 @@ template <int M>
 __device__ __forceinline__ void tile_twist(uint32_t *S, uint32_t T, const TileGeom &g,
                                            const uint32_t *__restrict__ tw_d, uint32_t d)
 {
-  for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
-    const uint32_t c = tw_d[g.pos(l) >> d];
-    if (c == 1u) continue;
-    const uint32_t sl = swz(l);
-    uint32_t a[M];
+  constexpr int U = 4;   // constants of four positions are fetched before the first multiply
+  for (uint32_t base = threadIdx.x; base < T; base += U * blockDim.x) {
+    uint32_t c[U];
 #pragma unroll
-    for (int b = 0; b < M; ++b) a[b] = S[b * T + sl];
-    bs_mul_scalar<M>(a, c);
+    for (int u = 0; u < U; ++u) {
+      const uint32_t l = base + u * blockDim.x;
+      c[u] = (l < T) ? tw_d[g.pos(l) >> d] : 1u;
+    }
 #pragma unroll
-    for (int b = 0; b < M; ++b) S[b * T + sl] = a[b];
+    for (int u = 0; u < U; ++u) {
+      if (c[u] == 1u) continue;
+      const uint32_t sl = swz(base + u * blockDim.x);
+      uint32_t a[M];
+#pragma unroll
+      for (int b = 0; b < M; ++b) a[b] = S[b * T + sl];
+      bs_mul_scalar<M>(a, c[u]);
+#pragma unroll
+      for (int b = 0; b < M; ++b) S[b * T + sl] = a[b];
+    }
   }
 }
 
@@ -336,7 +375,7 @@ __device__ __forceinline__ void tile_butterfly_r4(uint32_t *S, uint32_t T, uint3
 }
 
 // Runs the ops of a pass on a tile.  Consecutive Taylor levels of one depth on adjacent bits are
-// fused four at a time, consecutive butterfly levels two at a time (register-resident radix
+// fused five at a time, consecutive butterfly levels two at a time (register-resident radix
 // blocks): fewer shared-memory round trips and barriers than one sweep per level.
 template <int M, class Epi = NoEpilogue>
 __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
@@ -353,15 +392,19 @@ __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t
     } else if (op.type == OP_TY) {
       // ops i .. i+c-1: same depth, lo and local bit both descending by one
       uint32_t c = 1;
-      while (c < 4 && i + c < desc.nops) {
+      while (c < 5 && i + c < desc.nops) {
         const PassOp nx = desc.ops[i + c];
         if (nx.type != OP_TY || nx.d != op.d || nx.lo + c != op.lo ||
             g.local_bit(nx.lo) + c != g.local_bit(op.lo) || g.local_bit(nx.lo + 1u) != g.local_bit(nx.lo) + 1u)
           break;
         c++;
       }
+      // (a six-bit group that reaches into the five lowest local bits cannot be made bank
+      // conflict free by the swizzle: keep those at four levels)
+      if (c == 5 && g.local_bit(op.lo) + 1u - c < 5u) c = 4;
       const uint32_t g0 = g.local_bit(op.lo) + 1u - c;   // local bit of the last level's lo
-      if (c == 4) tile_taylor_multi<M, 5>(S, T, t, g0);
+      if (c == 5) tile_taylor_multi<M, 6>(S, T, t, g0);
+      else if (c == 4) tile_taylor_multi<M, 5>(S, T, t, g0);
       else if (c == 3) tile_taylor_multi<M, 4>(S, T, t, g0);
       else if (c == 2) tile_taylor_multi<M, 3>(S, T, t, g0);
       else tile_taylor_multi<M, 2>(S, T, t, g0);
@@ -390,7 +433,7 @@ __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t
 // ---- one pass over every tile of every slab -----------------------------------------------
 // grid = (tiles per slab, slabs); dynamic smem = M * 2^t * 4 bytes.
 template <int M>
-__global__ void __launch_bounds__(BCHFFT_NT_PASS, 1)
+__global__ void __launch_bounds__(BCHFFT_NT_PASS, BCHFFT_MINB_PASS)
 k_gm_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t src_slab_words,
           size_t dst_slab_words, FftTables tab, PassDesc desc)
 {

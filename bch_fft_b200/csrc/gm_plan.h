@@ -47,6 +47,10 @@ struct GmConstants {
   std::vector<uint32_t> gam;      // concatenated gam[d][0 .. 2^(m-d-1))
   std::vector<uint32_t> tw_off;   // m entries
   std::vector<uint32_t> gam_off;  // m entries
+  std::vector<uint32_t> basis;    // beta_1 .. beta_m: evaluation point J is sum_i J_i beta_(i+1)
+  std::vector<uint32_t> pos_of_elem;  // field element k -> tile position holding P(k)
+  std::vector<uint32_t> elem_of_pos;  // inverse map
+  uint32_t twist_free = 0;        // bit d set: tau_d = 1, TW(d) is the identity
 };
 
 inline uint32_t bitrev_bits(uint32_t x, int bits)
@@ -56,11 +60,50 @@ inline uint32_t bitrev_bits(uint32_t x, int bits)
   return r;
 }
 
+// Solve y^2 + y = c over GF(2^m) (a GF(2)-linear system); returns false when Tr(c) = 1.
+template <class Mul>
+inline bool solve_artin_schreier(int m, Mul mul, uint32_t c, uint32_t *out)
+{
+  // echelon basis of the image of S(y) = y^2 + y, each vector with the y that produces it
+  std::vector<uint32_t> img(m, 0u), pre(m, 0u);
+  for (int b = 0; b < m; b++) {
+    uint32_t y = 1u << b, v = mul(y, y) ^ y;
+    for (int k = m - 1; k >= 0 && v; k--) {
+      if (!((v >> k) & 1u)) continue;
+      if (img[k]) {
+        v ^= img[k];
+        y ^= pre[k];
+      } else {
+        img[k] = v;
+        pre[k] = y;
+        v = 0;
+      }
+    }
+  }
+  uint32_t y = 0;
+  for (int k = m - 1; k >= 0 && c; k--) {
+    if (!((c >> k) & 1u)) continue;
+    if (!img[k]) return false;
+    c ^= img[k];
+    y ^= pre[k];
+  }
+  *out = y;
+  return c == 0;
+}
+
 // exp/log: the caller's TfiniteField tables (libbase/finite_field.c:19-48 layout:
 // exp[i] = x^i, log[0] = order).
+//
+// Choice of the evaluation basis.  The transform evaluates at every field element, and the
+// output is gathered through a permutation table anyway (exp order for po_result, natural order
+// for the clobbered p_poly), so the order in which the kernels enumerate the points is free.
+// We use a basis whose tail is a Cantor chain 1 = c_0, c_1, .., with c_k^2 + c_k = c_(k-1): every
+// depth whose last basis element is 1 needs no twist at all (tw[d] == 1).  The chain has length
+// 2^a for m = 2^a * odd: all 16 depths for GF(2^16) (multiplications drop from 1.5 n m to
+// 0.5 n m), 4 for GF(2^20), 1 for odd m.  The remaining basis elements are powers of x.
 inline GmConstants gm_constants(int m, const uint32_t *exp, const uint32_t *log)
 {
-  const uint32_t order = (1u << m) - 1u;
+  const uint32_t order = (1u << m) - 1u, n = 1u << m;
   auto mul = [&](uint32_t a, uint32_t b) -> uint32_t {
     if (!a || !b) return 0;
     uint32_t s = log[a] + log[b];
@@ -69,11 +112,52 @@ inline GmConstants gm_constants(int m, const uint32_t *exp, const uint32_t *log)
   };
   GmConstants c;
   c.m = m;
-  std::vector<uint32_t> basis(m);
-  for (int i = 0; i < m; i++) basis[i] = 1u << i;
+  std::vector<uint32_t> chain(1, 1u);
+  while ((int)chain.size() < m) {
+    uint32_t y;
+    if (!solve_artin_schreier(m, mul, chain.back(), &y)) break;
+    chain.push_back(y);
+  }
+  // basis = (fill .., chain reversed): beta_m = 1, beta_(m-1) = c_1, ...
+  std::vector<uint32_t> basis(m, 0u);
+  std::vector<uint32_t> ech(m, 0u);   // echelon form for the independence test
+  auto independent_insert = [&](uint32_t v) -> bool {
+    for (int k = m - 1; k >= 0 && v; k--) {
+      if (!((v >> k) & 1u)) continue;
+      if (ech[k]) v ^= ech[k];
+      else { ech[k] = v; return true; }
+    }
+    return false;
+  };
+  for (size_t k = 0; k < chain.size(); k++) {
+    independent_insert(chain[k]);
+    basis[m - 1 - k] = chain[k];
+  }
+  {
+    int slot = 0;
+    for (int b = 0; b < m && slot < m - (int)chain.size(); b++)
+      if (independent_insert(1u << b)) basis[slot++] = 1u << b;
+  }
+  c.basis = basis;
+  // point tables: natural index J over the basis <-> tile position bitrev(J)
+  c.pos_of_elem.assign(n, 0u);
+  c.elem_of_pos.assign(n, 0u);
+  {
+    std::vector<uint32_t> elem(n, 0u);
+    for (uint32_t J = 1; J < n; J++) {
+      const int low = __builtin_ctz(J);
+      elem[J] = elem[J & (J - 1u)] ^ basis[low];
+    }
+    for (uint32_t J = 0; J < n; J++) {
+      const uint32_t p = bitrev_bits(J, m);
+      c.elem_of_pos[p] = elem[J];
+      c.pos_of_elem[elem[J]] = p;
+    }
+  }
   for (int d = 0; d < m; d++) {
     const int k = m - d;
     const uint32_t tau = basis[k - 1];
+    if (tau == 1u) c.twist_free |= 1u << d;
     c.tw_off.push_back((uint32_t)c.tw.size());
     uint32_t pw = 1;
     for (uint32_t i = 0; i < (1u << k); i++) {
@@ -159,7 +243,7 @@ struct GmPlan {
 };
 
 // t_max: largest tile (log2 positions) that fits the CTA's shared memory for this M.
-inline GmPlan gm_plan(int m, int K, int t_max)
+inline GmPlan gm_plan(int m, int K, int t_max, uint32_t twist_free = 0u)
 {
   GmPlan plan;
   plan.m = m;
@@ -197,12 +281,14 @@ inline GmPlan gm_plan(int m, int K, int t_max)
   };
   std::vector<Item> fwd, bwd;
   for (int d = 0; d < K; d++) {
-    fwd.push_back({{OP_TW, (uint8_t)d, 0, 0}, 0u});
+    if (!((twist_free >> d) & 1u)) fwd.push_back({{OP_TW, (uint8_t)d, 0, 0}, 0u});
     for (int lo = K - 2; lo >= d; lo--) fwd.push_back({{OP_TY, (uint8_t)d, (uint8_t)lo, 0}, 3u << lo});
   }
   for (int d = K - 1; d >= 0; d--) bwd.push_back({{OP_BF, (uint8_t)d, 0, 0}, 1u << d});
-  if (K == m && m <= t_max) {
-    // whole transform fits one tile: a single in-place pass does everything
+  if (K == m) {
+    // full-degree input: forward and backward phases work in place on the same buffer, so they
+    // form one op stream (the last forward ops and the first butterflies usually share a pass;
+    // a transform that fits one tile is a single pass)
     std::vector<Item> all = fwd;
     all.insert(all.end(), bwd.begin(), bwd.end());
     plan.first_backward = 0;

@@ -17,12 +17,12 @@ def dump(title, fn="bchfft_debug_trace"):
         prev = clk
 # FFT m=16, 64 polys
 f = host.create_binary_finite_field(16)
-polys = synth.random_polys(16, 64, 1)
+polys = synth.random_polys(16, 1024, 1)
 dump("warm")
 f.additive_fft_batch(polys, 65535); dump("discard")
 code = host.bch_gen_code(8191, 33)
 bits = (synth.splitmix64(1, 8*code.data_bits) & np.uint64(1)).astype(np.uint32).reshape(8,-1)
 pool = np.stack([code.encode(b) for b in bits])
-words,_ = synth.corrupt_codewords(pool, 8191, 16, 4096, 5)
+words,_ = synth.corrupt_codewords(pool, 8191, 16, 65536, 5)
 code.decode_batch(words); dump("discard", "bchfft_debug_trace_bch")
 code.decode_batch(words); dump("decode: k_locate CTA (0,0)", "bchfft_debug_trace_bch")
