@@ -221,43 +221,79 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, const int32_t *__restrict
 // ---- root search ----------------------------------------------------------------------------
 // The error locator of every codeword is evaluated at all 2^M field points with the truncated
 // additive FFT (the device counterpart of bch.c:406-490's FFT path, with the reference's
-// low-degree shortcut of additive_fft.c:103-110 taken to its conclusion):
-//   k_elp_fwd   bitslice the locator coefficients of 2^sb slabs per CTA and run the forward
-//               phase (twists + Taylor expansions) on the 2^K coefficients, K = ceil(log2(t+1))
-//   k_locate    per tile of 2^t positions: broadcast the 2^K forward values over the cosets,
-//               K butterfly levels, zero test fused into the last level
+// low-degree shortcut of additive_fft.c:103-110 taken to its conclusion).  The cost of the
+// truncated transform is K = ceil(log2(L+1)) butterfly levels over all points, so codewords are
+// first sorted into buckets by K and packed into slabs per bucket: a slab of degree-3 locators
+// runs 2 levels, not the 5 a degree-16 locator needs.
+//   k_bucket    counting sort of the codewords that need a root search by K
+//   k_elp_fwd   per bucket: bitslice the locator coefficients of 2^sb slabs per CTA and run the
+//               forward phase (twists + Taylor expansions) on the 2^K coefficients
+//   k_locate    one launch over the slabs of all buckets: per tile of 2^t positions broadcast
+//               the 2^K forward values over the cosets, K butterfly levels, zero test fused
+//               into the last level
 // A zero at the tile position that holds the field point k = x^i != 0 is an error at bit `order - i`
 // (bch.c:479-488, including the bit-0 quirk: i = 0 reports position `order`).
 
-// grid = ceil(nslabs / 2^sb); dynamic smem = M * 2^(K+sb) words.
-// Fout: [slab][2^K][PS]; active[slab] = mask of codewords that take part (flagged and L <= tcap).
+constexpr int kMaxBuckets = 12;   // K = 1 .. 12
+
+__device__ __forceinline__ uint32_t locator_bucket(uint32_t L)   // ceil(log2(L + 1))
+{
+  return 32u - (uint32_t)__clz((int)L);
+}
+
+// counts: [kMaxBuckets + 1] zero-initialised; lists: [kMaxBuckets + 1][batch] codeword indices.
+// Codewords with nothing to locate (not flagged, L = 0: constant locator, or L > tcap) stay out.
+__global__ void k_bucket(const int32_t *__restrict__ flag, const uint32_t *__restrict__ Lin,
+                         uint32_t tcap, uint32_t batch, uint32_t *__restrict__ counts,
+                         uint32_t *__restrict__ lists)
+{
+  __shared__ uint32_t hist[kMaxBuckets + 1], base[kMaxBuckets + 1];
+  if (threadIdx.x <= kMaxBuckets) hist[threadIdx.x] = 0u;
+  __syncthreads();
+  const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t b = 0u, rank = 0u;
+  if (cw < batch && flag[cw]) {
+    const uint32_t L = Lin[cw];
+    if (L >= 1u && L <= tcap) b = locator_bucket(L);
+  }
+  if (b) rank = atomicAdd(&hist[b], 1u);
+  __syncthreads();
+  if (threadIdx.x >= 1 && threadIdx.x <= kMaxBuckets && hist[threadIdx.x])
+    base[threadIdx.x] = atomicAdd(&counts[threadIdx.x], hist[threadIdx.x]);
+  __syncthreads();
+  if (b) lists[(size_t)b * batch + base[b] + rank] = cw;
+}
+
+// Forward phase for bucket K = fwd.dom_bits.  grid = worst-case number of slab groups (CTAs
+// beyond the bucket's population exit); dynamic smem = M * 2^(K+sb) words.
+// Fout: [virtual slab][2^Kmax][PS] with virtual slab = vbase(bucket) + slab in bucket.
 template <int M>
 __global__ void __launch_bounds__(256)
-k_elp_fwd(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin,
-          const int32_t *__restrict__ flag, uint32_t d, uint32_t tcap, uint32_t batch, uint32_t nslabs,
-          uint32_t sb, FftTables tab, PassDesc fwd, uint32_t *__restrict__ Fout,
-          uint32_t *__restrict__ active)
+k_elp_fwd(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin, uint32_t d,
+          const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists, uint32_t batch,
+          uint32_t sb, uint32_t kmax, FftTables tab, PassDesc fwd, uint32_t *__restrict__ Fout)
 {
   constexpr int PS = plane_stride(M);
   BCHFFT_DYN_SMEM(uint32_t, S);
   const uint32_t K = fwd.dom_bits, TK = 1u << K, tt = K + sb, T = 1u << tt;
+  const uint32_t pop = counts[K], nslabs = (pop + 31u) >> 5;
   const uint32_t slab0 = blockIdx.x << sb;
+  if (slab0 >= nslabs) return;
+  uint32_t vbase = 0u;
+  for (uint32_t k = 1; k < K; ++k) vbase += (counts[k] + 31u) >> 5;
+  const uint32_t *list = lists + (size_t)K * batch;
   // coefficient index i of the 32 codewords of a slab -> M plane words.  Coefficients above L
   // are not part of the polynomial (bch.c:444-445, 466).
   for (uint32_t idx = threadIdx.x; idx < T; idx += blockDim.x) {
     const uint32_t slab = slab0 + (idx >> K), i = idx & (TK - 1u);
     uint32_t x[32];
-    uint32_t act = 0u;
 #pragma unroll
     for (int l = 0; l < 32; ++l) {
-      const uint32_t cw = slab * 32u + l;
+      const uint32_t at = slab * 32u + l;
       uint32_t v = 0u;
-      if (cw < batch && flag[cw]) {
-        const uint32_t L = Lin[cw];
-        if (L <= tcap) {
-          act |= 1u << l;
-          if (i <= L) v = elp[(size_t)cw * (d + 1) + i];
-        }
+      if (at < pop) {
+        const uint32_t cw = list[at];
+        if (i <= Lin[cw]) v = elp[(size_t)cw * (d + 1) + i];
       }
       x[l] = v;
     }
@@ -265,7 +301,6 @@ k_elp_fwd(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin,
     const uint32_t sl = swz(idx);
 #pragma unroll
     for (int b = 0; b < M; ++b) S[b * T + sl] = x[b];
-    if (i == 0 && slab < nslabs) active[slab] = act;
   }
   __syncthreads();
   TileGeom g;
@@ -279,7 +314,7 @@ k_elp_fwd(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin,
   for (uint32_t idx = threadIdx.x; idx < T; idx += blockDim.x) {
     const uint32_t slab = slab0 + (idx >> K), i = idx & (TK - 1u);
     if (slab >= nslabs) continue;
-    uint4 *out = reinterpret_cast<uint4 *>(Fout + ((size_t)slab * TK + i) * PS);
+    uint4 *out = reinterpret_cast<uint4 *>(Fout + (((size_t)(vbase + slab) << kmax) + i) * PS);
     const uint32_t sl = swz(idx);
 #pragma unroll
     for (int v = 0; v < PS / 4; ++v) {
@@ -298,8 +333,9 @@ template <int M>
 struct RootEpilogue {
   const TileGeom *g;
   const uint32_t *errloc;   // tile position -> reported error position (0xFFFFFFFF: the point 0)
+  const uint32_t *list;     // codeword index of every lane of the slab
   uint32_t *count, *positions;
-  uint32_t active, slab, pos_stride;
+  uint32_t active, pos_stride;
   __device__ __forceinline__ void operator()(uint32_t l, const uint32_t *v) const
   {
     uint32_t nz = 0u;
@@ -312,36 +348,47 @@ struct RootEpilogue {
     while (roots) {
       const uint32_t lane = (uint32_t)__ffs((int)roots) - 1u;
       roots &= roots - 1u;
-      const uint32_t cw = slab * 32u + lane;
+      const uint32_t cw = list[lane];
       const uint32_t idx = atomicAdd(&count[cw], 1u);
       if (idx < pos_stride) positions[(size_t)cw * pos_stride + idx] = where;
     }
   }
 };
 
-// grid = (tiles per slab, slabs); dynamic smem = M * 2^t words.
+// grid = (tiles per slab, upper bound of the virtual slab count); dynamic smem = M * 2^t words.
+// bwd_descs[K]: the K butterfly levels on a tile of 2^t positions.
 template <int M>
 __global__ void __launch_bounds__(BCHFFT_NT_LOC, BCHFFT_MINB_LOC)
-k_locate(const uint32_t *__restrict__ F, const uint32_t *__restrict__ active_in, FftTables tab,
-         PassDesc bwd, uint32_t K, const uint32_t *__restrict__ errloc, uint32_t *__restrict__ count,
-         uint32_t *__restrict__ positions, uint32_t pos_stride)
+k_locate(const uint32_t *__restrict__ F, const uint32_t *__restrict__ counts,
+         const uint32_t *__restrict__ lists, uint32_t batch, uint32_t kmax, FftTables tab,
+         const PassDesc *__restrict__ bwd_descs, const uint32_t *__restrict__ errloc,
+         uint32_t *__restrict__ count, uint32_t *__restrict__ positions, uint32_t pos_stride)
 {
   constexpr int PS = plane_stride(M);
   BCHFFT_DYN_SMEM(uint32_t, S);
-  const uint32_t TK = 1u << K, T = 1u << bwd.t;
-  const uint32_t slab = blockIdx.y;
-  const uint32_t active = active_in[slab];
-  if (active == 0u) return;   // nothing to locate in this slab (uniform across the CTA)
+  // virtual slab -> (bucket K, slab within the bucket)
+  uint32_t v = blockIdx.y, K = 1u;
+  for (; K <= kmax; ++K) {
+    const uint32_t ns = (counts[K] + 31u) >> 5;
+    if (v < ns) break;
+    v -= ns;
+  }
+  if (K > kmax) return;   // beyond the last populated slab (uniform across the CTA)
+  const uint32_t pop = counts[K];
+  const uint32_t lanes = pop - v * 32u;
+  const uint32_t active = lanes >= 32u ? 0xFFFFFFFFu : ((1u << lanes) - 1u);
+  const PassDesc &bwd = bwd_descs[K];
+  const uint32_t T = 1u << bwd.t;
   const TileGeom g = tile_geom(bwd, blockIdx.x);
-  tile_load<M>(S, T, F + (size_t)slab * TK * PS, g, TK - 1u);
+  tile_load<M>(S, T, F + ((size_t)blockIdx.y << kmax) * PS, g, (1u << K) - 1u);
   __syncthreads();
   RootEpilogue<M> epi;
   epi.g = &g;
   epi.errloc = errloc;
+  epi.list = lists + (size_t)K * batch + v * 32u;
   epi.count = count;
   epi.positions = positions;
   epi.active = active;
-  epi.slab = slab;
   epi.pos_stride = pos_stride;
   tile_run_ops<M, RootEpilogue<M>>(S, T, bwd.t, g, tab, bwd, &epi);
 }

@@ -18,6 +18,8 @@ struct bchfft_code {
   struct WorkSet {
     bchfft::DeviceBuffer scratch, fwd_buf, words, ok, corr;
     cudaStream_t stream = nullptr;
+    int descs_t = -1, descs_kmax = -1;   // butterfly descriptors currently uploaded in fwd_buf
+    void *descs_at = nullptr;
   } work[4];
 };
 
@@ -141,37 +143,59 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
                          cudaStream_t st)
 {
   constexpr int PS = plane_stride(M);
-  const int K = ceil_log2u(tcap + 1u);
+  const int kmax = ceil_log2u(tcap + 1u) < 1 ? 1 : ceil_log2u(tcap + 1u);
   // half of the largest tile that fits an SM, so that two CTAs are resident (BCHFFT_MINB_LOC)
   int t = c->f->t_max - 1;
-  if (t < K) t = K;
+  if (t < kmax) t = kmax;
   if (t > M) t = M;
   const char *tenv = getenv("BCHFFT_LOCATE_T");
-  if (tenv && atoi(tenv) >= K && atoi(tenv) <= c->f->t_max && atoi(tenv) <= M) t = atoi(tenv);
-  if (K > t || K > M) {
+  if (tenv && atoi(tenv) >= kmax && atoi(tenv) <= c->f->t_max && atoi(tenv) <= M) t = atoi(tenv);
+  if (kmax > t || kmax > M || kmax > kMaxBuckets || t > c->f->t_max) {
     set_error("bch locate: error-locator degree bound %u too large for one shared-memory tile", tcap);
     return BCHFFT_ERR_UNSUPPORTED;
   }
-  PassDesc fwd, bwd;
-  locate_descs(M, K, t, c->f->twist_free, fwd, bwd);
   const unsigned ns = (unsigned)((cnt + 31) / 32);
-  int rc = w.fwd_buf.reserve(((size_t)ns << K) * PS * 4 + (size_t)ns * 4 + 64);
+  const unsigned nvirt = ns + (unsigned)kmax;           // sum_K ceil(count_K / 32) <= ns + kmax
+  // work buffer: butterfly descriptors, bucket counts, bucket lists, forward values
+  const size_t desc_bytes = (sizeof(PassDesc) * (kMaxBuckets + 1) + 255) & ~(size_t)255;
+  const size_t f_words = ((size_t)nvirt << kmax) * PS;
+  const size_t need = desc_bytes + ((kMaxBuckets + 1) + (size_t)(kMaxBuckets + 1) * cnt + f_words) * 4 + 256;
+  int rc = w.fwd_buf.reserve(need);
   if (rc) return rc;
-  uint32_t *F = (uint32_t *)w.fwd_buf.p;
-  uint32_t *active = F + ((size_t)ns << K) * PS;
-  // forward phase: 2^sb slabs per CTA so that a CTA has 256 coefficient columns to work on
-  uint32_t sb = 0;
-  while ((1u << (K + sb)) < 256u) sb++;
-  const size_t smem_f = sizeof(uint32_t) * M * ((size_t)1 << (K + sb));
-  BCHFFT_ENSURE_SMEM(k_elp_fwd<M>, c->f->device, smem_f);
-  BCHFFT_RUN(k_elp_fwd<M>, dim3((ns + (1u << sb) - 1u) >> sb), dim3(256), smem_f, st,
-             (const uint32_t *)s.elp, (const uint32_t *)s.L, (const int32_t *)s.flag, c->d, tcap,
-             (uint32_t)cnt, (uint32_t)ns, sb, c->f->tab, fwd, F, active);
+  PassDesc *d_descs = (PassDesc *)w.fwd_buf.p;
+  uint32_t *counts = (uint32_t *)((char *)w.fwd_buf.p + desc_bytes);
+  uint32_t *lists = counts + (kMaxBuckets + 1);
+  uint32_t *F = lists + (((size_t)(kMaxBuckets + 1) * cnt + 3) & ~(size_t)3);
+  std::vector<PassDesc> fwd(kmax + 1), bwd(kMaxBuckets + 1);
+  for (int K = 1; K <= kmax; K++) locate_descs(M, K, t, c->f->twist_free, fwd[K], bwd[K]);
+  if (w.descs_t != t || w.descs_kmax != kmax || w.descs_at != (void *)d_descs) {
+    // the descriptors only depend on (t, kmax): uploaded once per work buffer
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(d_descs, bwd.data(), sizeof(PassDesc) * (kMaxBuckets + 1),
+                                    cudaMemcpyHostToDevice, st));
+    BCHFFT_CUDA_TRY(cudaStreamSynchronize(st));          // bwd is a stack object
+    w.descs_t = t;
+    w.descs_kmax = kmax;
+    w.descs_at = d_descs;
+  }
+  BCHFFT_CUDA_TRY(cudaMemsetAsync(counts, 0, (kMaxBuckets + 1) * 4, st));
+  BCHFFT_RUN(k_bucket, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, (const int32_t *)s.flag,
+             (const uint32_t *)s.L, tcap, (uint32_t)cnt, counts, lists);
+  for (int K = 1; K <= kmax; K++) {
+    // forward phase: 2^sb slabs per CTA so that a CTA has 256 coefficient columns to work on
+    uint32_t sb = 0;
+    while ((1u << (K + sb)) < 256u) sb++;
+    const size_t smem_f = sizeof(uint32_t) * M * ((size_t)1 << (K + sb));
+    BCHFFT_ENSURE_SMEM(k_elp_fwd<M>, c->f->device, smem_f);
+    BCHFFT_RUN(k_elp_fwd<M>, dim3((ns + (1u << sb) - 1u) >> sb), dim3(256), smem_f, st,
+               (const uint32_t *)s.elp, (const uint32_t *)s.L, c->d, (const uint32_t *)counts,
+               (const uint32_t *)lists, (uint32_t)cnt, sb, (uint32_t)kmax, c->f->tab, fwd[K], F);
+  }
   const size_t smem = sizeof(uint32_t) * M * ((size_t)1 << t);
   BCHFFT_ENSURE_SMEM(k_locate<M>, c->f->device, smem);
-  BCHFFT_RUN(k_locate<M>, dim3(1u << (M - t), ns), dim3(kNtLoc), smem, st, (const uint32_t *)F,
-             (const uint32_t *)active, c->f->tab, bwd, (uint32_t)K, (const uint32_t *)c->f->d_errloc,
-             s.count, s.positions, s.pos_stride);
+  BCHFFT_RUN(k_locate<M>, dim3(1u << (M - t), nvirt), dim3(kNtLoc), smem, st, (const uint32_t *)F,
+             (const uint32_t *)counts, (const uint32_t *)lists, (uint32_t)cnt, (uint32_t)kmax, c->f->tab,
+             (const PassDesc *)d_descs, (const uint32_t *)c->f->d_errloc, s.count, s.positions,
+             s.pos_stride);
   return BCHFFT_OK;
 }
 
