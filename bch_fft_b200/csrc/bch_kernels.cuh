@@ -36,10 +36,11 @@ k_syndrome(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32
   const uint32_t slab = blockIdx.y;
   const uint32_t pos0 = blockIdx.x * chunk_pos;
   const uint32_t nsub = chunk_pos / kSynSub;
-  // planes[p + p / kSynSub]: one word of padding per sub-chunk keeps items of different
-  // sub-chunks on different banks
+  // planes[p + p / 32]: one word of padding per 32 positions keeps both the transposing stores
+  // of phase A (lanes 32 positions apart) and the loads of phase B (lanes of different
+  // sub-chunks) on distinct banks
   uint32_t *planes = smem;
-  uint32_t *sacc = smem + chunk_pos + nsub;  // [nodd][M]
+  uint32_t *sacc = smem + chunk_pos + chunk_pos / 32;  // [nodd][M]
   __shared__ uint32_t s_par;
   if (threadIdx.x == 0) s_par = 0u;
   for (uint32_t i = threadIdx.x; i < nodd * M; i += blockDim.x) sacc[i] = 0u;
@@ -66,8 +67,7 @@ k_syndrome(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32
     transpose32(x);
 #pragma unroll
     for (int b = 0; b < 32; ++b) {
-      const uint32_t p = g * 32u + b;
-      planes[p + p / kSynSub] = x[b];
+      planes[g * 33u + b] = x[b];
       par ^= x[b];
     }
   }
@@ -84,9 +84,9 @@ k_syndrome(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32
       tm[b] = 0u - ((tp >> b) & 1u);
       s[b] = 0u;
     }
-    const uint32_t *src = planes + q * (kSynSub + 1);
+    const uint32_t *src = planes + q * (kSynSub + kSynSub / 32);
     for (int p = kSynSub - 1; p >= 0; --p) {
-      const uint32_t in = src[p];
+      const uint32_t in = src[p + (p >> 5)];
       const uint32_t fb = s[M - 1];
 #pragma unroll
       for (int b = M - 1; b >= 1; --b) s[b] = s[b - 1] ^ (fb & tm[b]);

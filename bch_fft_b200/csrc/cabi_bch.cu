@@ -115,7 +115,7 @@ static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, 
                            cudaStream_t st)
 {
   const unsigned ns = (unsigned)((cnt + 31) / 32);
-  const size_t smem = sizeof(uint32_t) * ((size_t)c->chunk_pos + c->chunk_pos / kSynSub + (size_t)c->nodd * M);
+  const size_t smem = sizeof(uint32_t) * ((size_t)c->chunk_pos + c->chunk_pos / 32 + (size_t)c->nodd * M);
   BCHFFT_ENSURE_SMEM(k_syndrome<M>, c->f->device, smem);
   BCHFFT_RUN(k_syndrome<M>, dim3(c->nchunks, ns), dim3(kNtSyn), smem, st,
                 (const uint32_t *)d_words, c->wpc * 2u, c->length, (uint32_t)cnt, c->chunk_pos,
@@ -165,7 +165,8 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
   PassDesc *d_descs = (PassDesc *)w.fwd_buf.p;
   uint32_t *counts = (uint32_t *)((char *)w.fwd_buf.p + desc_bytes);
   uint32_t *lists = counts + (kMaxBuckets + 1);
-  uint32_t *F = lists + (((size_t)(kMaxBuckets + 1) * cnt + 3) & ~(size_t)3);
+  // forward values are read and written as 16-byte vectors
+  uint32_t *F = (uint32_t *)(((uintptr_t)(lists + (size_t)(kMaxBuckets + 1) * cnt) + 15) & ~(uintptr_t)15);
   std::vector<PassDesc> fwd(kmax + 1), bwd(kMaxBuckets + 1);
   for (int K = 1; K <= kmax; K++) locate_descs(M, K, t, c->f->twist_free, fwd[K], bwd[K]);
   if (w.descs_t != t || w.descs_kmax != kmax || w.descs_at != (void *)d_descs) {
@@ -304,7 +305,7 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
   // position chunk per CTA: as much of the codeword as fits next to the accumulators
   size_t budget = ((size_t)200 * 1024) / 4 - (size_t)c->nodd * M;
   uint32_t chunk = 1u << 15;
-  while (chunk > (uint32_t)kSynSub && (chunk + chunk / kSynSub > budget || chunk / 2 >= npos)) chunk >>= 1;
+  while (chunk > (uint32_t)kSynSub && (chunk + chunk / 32 > budget || chunk / 2 >= npos)) chunk >>= 1;
   c->chunk_pos = chunk;
   c->nchunks = (npos + chunk - 1u) / chunk;
   c->nsub_total = c->nchunks * (chunk / kSynSub);

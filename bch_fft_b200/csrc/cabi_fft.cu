@@ -41,8 +41,9 @@ static int fft_run(bchfft_field *f, DeviceBuffer &ws, const uint32_t *d_polys, s
   BCHFFT_ENSURE_SMEM(k_gm_pass<M>, f->device, ((size_t)4 * M) << f->t_max);
   const int nt_io = 128;
 #ifdef BCHFFT_EMU
-  const int nt_pass = 32;
+  const int nt_pass = 32, nt_ty = 32;
 #else
+  const int nt_ty = 256;
   const int nt_pass = BCHFFT_NT_PASS;
 #endif
   for (size_t s0 = 0; s0 < nslabs; s0 += chunk) {
@@ -63,6 +64,16 @@ static int fft_run(bchfft_field *f, DeviceBuffer &ws, const uint32_t *d_polys, s
       const size_t src_words = (bw && !first_bw) ? bwd_words : fwd_words;
       const size_t dst_words = bw ? bwd_words : fwd_words;
       dim3 grid(1u << (pd.dom_bits - pd.t), (unsigned)cs);
+      bool ty_only = pd.nops > 0 && psrc == pdst && PS % 8 == 0 && pd.src_mask == 0xFFFFFFFFu;
+      for (uint32_t k = 0; k < pd.nops && ty_only; k++) ty_only = pd.ops[k].type == OP_TY;
+      if (ty_only) {
+        // XOR-only pass: eight planes per CTA (see k_ty_pass)
+        const size_t smem8 = ((size_t)4 * 8) << pd.t;
+        BCHFFT_ENSURE_SMEM(k_ty_pass<PS>, f->device, smem8);
+        grid.z = PS / 8;
+        BCHFFT_RUN(k_ty_pass<PS>, grid, dim3(nt_ty), smem8, stream, pdst, dst_words, pd);
+        continue;
+      }
       const size_t smem = ((size_t)4 * M) << pd.t;
       BCHFFT_RUN(k_gm_pass<M>, grid, dim3(nt_pass), smem, stream, psrc, pdst, src_words,
                     dst_words, f->tab, pd);

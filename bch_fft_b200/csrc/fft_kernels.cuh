@@ -253,12 +253,13 @@ __device__ __forceinline__ void tile_twist(uint32_t *S, uint32_t T, const TileGe
 // R-1 consecutive Taylor-expansion levels (at x^2+x) on local bits [g0, g0+R): the level on
 // bit pair (lv+1, lv), lv = R-2 .. 0, does Q2 ^= Q3 then Q1 ^= Q2.  XOR only and plane-wise, so
 // a work item is (plane, block of 2^R positions) held in registers.
-template <int M, int R>
-__device__ __forceinline__ void tile_taylor_multi(uint32_t *S, uint32_t T, uint32_t t, uint32_t g0)
+template <int R>
+__device__ __forceinline__ void tile_taylor_multi(uint32_t *S, uint32_t T, uint32_t t, uint32_t g0,
+                                                  uint32_t nplanes)
 {
   const SweepMap map = make_sweep_map(t, g0, R);
   const uint32_t blocks = T >> R;
-  for (uint32_t idx = threadIdx.x; idx < blocks * M; idx += blockDim.x) {
+  for (uint32_t idx = threadIdx.x; idx < blocks * nplanes; idx += blockDim.x) {
     const uint32_t plane = idx / blocks, w = idx - plane * blocks;
     const uint32_t base = map.pos(w);
     uint32_t *row = S + plane * T;
@@ -284,6 +285,35 @@ __device__ __forceinline__ void tile_taylor_multi(uint32_t *S, uint32_t T, uint3
 struct NoEpilogue {
   __device__ __forceinline__ void operator()(uint32_t, const uint32_t *) const {}
 };
+
+__device__ __forceinline__ void tile_taylor_dispatch(uint32_t *S, uint32_t T, uint32_t t, uint32_t g0,
+                                                     uint32_t levels, uint32_t nplanes)
+{
+  if (levels == 5) tile_taylor_multi<6>(S, T, t, g0, nplanes);
+  else if (levels == 4) tile_taylor_multi<5>(S, T, t, g0, nplanes);
+  else if (levels == 3) tile_taylor_multi<4>(S, T, t, g0, nplanes);
+  else if (levels == 2) tile_taylor_multi<3>(S, T, t, g0, nplanes);
+  else tile_taylor_multi<2>(S, T, t, g0, nplanes);
+}
+
+// number of consecutive Taylor ops starting at op i that one register-resident sweep can take:
+// same depth, lo and local bit both descending by one, at most five levels (a six-bit group
+// that reaches into the five lowest local bits cannot be made bank-conflict free by the
+// swizzle: those stay at four)
+__device__ __forceinline__ uint32_t taylor_run(const PassDesc &desc, const TileGeom &g, uint32_t i)
+{
+  const PassOp op = desc.ops[i];
+  uint32_t c = 1;
+  while (c < 5 && i + c < desc.nops) {
+    const PassOp nx = desc.ops[i + c];
+    if (nx.type != OP_TY || nx.d != op.d || nx.lo + c != op.lo ||
+        g.local_bit(nx.lo) + c != g.local_bit(op.lo))
+      break;
+    c++;
+  }
+  if (c == 5 && g.local_bit(op.lo) + 1u - c < 5u) c = 4;
+  return c;
+}
 
 // BF(d): lo' = lo + gam[d][p >> (d+1)] * hi ; hi' = lo' + hi
 template <int M, class Epi>
@@ -390,24 +420,9 @@ __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t
       tile_twist<M>(S, T, g, tab.tw + tab.tw_off[op.d], op.d);
       i += 1;
     } else if (op.type == OP_TY) {
-      // ops i .. i+c-1: same depth, lo and local bit both descending by one
-      uint32_t c = 1;
-      while (c < 5 && i + c < desc.nops) {
-        const PassOp nx = desc.ops[i + c];
-        if (nx.type != OP_TY || nx.d != op.d || nx.lo + c != op.lo ||
-            g.local_bit(nx.lo) + c != g.local_bit(op.lo) || g.local_bit(nx.lo + 1u) != g.local_bit(nx.lo) + 1u)
-          break;
-        c++;
-      }
-      // (a six-bit group that reaches into the five lowest local bits cannot be made bank
-      // conflict free by the swizzle: keep those at four levels)
-      if (c == 5 && g.local_bit(op.lo) + 1u - c < 5u) c = 4;
+      const uint32_t c = taylor_run(desc, g, i);
       const uint32_t g0 = g.local_bit(op.lo) + 1u - c;   // local bit of the last level's lo
-      if (c == 5) tile_taylor_multi<M, 6>(S, T, t, g0);
-      else if (c == 4) tile_taylor_multi<M, 5>(S, T, t, g0);
-      else if (c == 3) tile_taylor_multi<M, 4>(S, T, t, g0);
-      else if (c == 2) tile_taylor_multi<M, 3>(S, T, t, g0);
-      else tile_taylor_multi<M, 2>(S, T, t, g0);
+      tile_taylor_dispatch(S, T, t, g0, c, (uint32_t)M);
       i += c;
     } else {
       bool pair = false;
@@ -447,6 +462,65 @@ k_gm_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t s
   BCHFFT_MARK(2);
   tile_store<M>(S, T, dst + (size_t)blockIdx.y * dst_slab_words, g);
   BCHFFT_MARK(3);
+}
+
+// ---- Taylor-only pass on a group of planes --------------------------------------------------
+// A pass that contains only Taylor levels (XOR only, plane-wise) does not need whole elements:
+// each CTA takes MP = 8 of the PS plane words of every position of the tile (one 32-byte
+// sector), so its tile is half the size and two or three CTAs are resident per SM -- the
+// load / sweep / store phases of neighbouring CTAs overlap.  grid = (tiles, slabs, PS / 8).
+template <int PSW>
+__global__ void __launch_bounds__(256, 2)
+k_ty_pass(uint32_t *__restrict__ buf, size_t slab_words, PassDesc desc)
+{
+  constexpr int MP = 8;
+  BCHFFT_DYN_SMEM(uint32_t, S);
+  const uint32_t T = 1u << desc.t;
+  const TileGeom g = tile_geom(desc, blockIdx.x);
+  uint32_t *base = buf + (size_t)blockIdx.y * slab_words + blockIdx.z * MP;
+  constexpr int U = 4;
+  for (uint32_t b0 = threadIdx.x; b0 < T; b0 += U * blockDim.x) {
+    uint4 q[U][2];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t l = b0 + u * blockDim.x;
+      if (l < T) {
+        const uint4 *in = reinterpret_cast<const uint4 *>(base + (size_t)g.pos(l) * PSW);
+        q[u][0] = in[0];
+        q[u][1] = in[1];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t l = b0 + u * blockDim.x;
+      if (l < T) {
+        const uint32_t sl = swz(l);
+        S[0 * T + sl] = q[u][0].x;
+        S[1 * T + sl] = q[u][0].y;
+        S[2 * T + sl] = q[u][0].z;
+        S[3 * T + sl] = q[u][0].w;
+        S[4 * T + sl] = q[u][1].x;
+        S[5 * T + sl] = q[u][1].y;
+        S[6 * T + sl] = q[u][1].z;
+        S[7 * T + sl] = q[u][1].w;
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t i = 0;
+  while (i < desc.nops) {
+    const uint32_t c = taylor_run(desc, g, i);
+    const uint32_t g0 = g.local_bit(desc.ops[i].lo) + 1u - c;
+    tile_taylor_dispatch(S, T, desc.t, g0, c, (uint32_t)MP);
+    i += c;
+    __syncthreads();
+  }
+  for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
+    const uint32_t sl = swz(l);
+    uint4 *out = reinterpret_cast<uint4 *>(base + (size_t)g.pos(l) * PSW);
+    out[0] = make_uint4(S[0 * T + sl], S[1 * T + sl], S[2 * T + sl], S[3 * T + sl]);
+    out[1] = make_uint4(S[4 * T + sl], S[5 * T + sl], S[6 * T + sl], S[7 * T + sl]);
+  }
 }
 
 // ---- bitsliced slabs -> AoS u32, through a position permutation ---------------------------
