@@ -30,6 +30,14 @@
 #ifndef BCHFFT_MINB_PASS
 #define BCHFFT_MINB_PASS 1
 #endif
+// Taylor-only passes: resident CTAs per SM and Taylor levels fused per sweep (2^(levels+1)
+// registers of data per thread)
+#ifndef BCHFFT_MINB_TY
+#define BCHFFT_MINB_TY 3
+#endif
+#ifndef BCHFFT_TY_LEVELS
+#define BCHFFT_TY_LEVELS 4
+#endif
 #ifndef BCHFFT_NT_LOC
 #define BCHFFT_NT_LOC 256
 #endif

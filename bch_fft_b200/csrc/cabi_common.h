@@ -41,17 +41,13 @@ void prof_after();
   } while (0)
 
 // Opt a kernel in to `bytes` of dynamic shared memory.  The attribute belongs to the function
-// (per device), not to one of our contexts, so the high-water mark is kept per call site and
-// device and is only ever raised.
+// (per device), not to one of our contexts or call sites, so one process-wide table keeps the
+// high-water mark per (function, device) and the attribute is only ever raised.
+int ensure_smem(const void *kernel, int device, size_t bytes);
 #define BCHFFT_ENSURE_SMEM(kernel, device, bytes)                                          \
   do {                                                                                     \
-    static size_t hw_[64] = {0};                                                           \
-    const int dv_ = (device) & 63;                                                         \
-    if ((size_t)(bytes) > hw_[dv_]) {                                                      \
-      BCHFFT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           (int)(bytes)));                                 \
-      hw_[dv_] = (size_t)(bytes);                                                          \
-    }                                                                                      \
+    int rc_smem_ = bchfft::ensure_smem((const void *)(kernel), (device), (size_t)(bytes)); \
+    if (rc_smem_) return rc_smem_;                                                         \
   } while (0)
 
 // field degrees the kernels are instantiated for

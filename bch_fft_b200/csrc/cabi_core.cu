@@ -36,6 +36,21 @@ void DeviceBuffer::release()
   bytes = 0;
 }
 
+int ensure_smem(const void *kernel, int device, size_t bytes)
+{
+  static std::map<std::pair<const void *, int>, size_t> high_water;
+  size_t &hw = high_water[std::make_pair(kernel, device)];
+  if (bytes <= hw) return BCHFFT_OK;
+#ifdef BCHFFT_EMU
+  hw = bytes;
+  return BCHFFT_OK;
+#else
+  BCHFFT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  hw = bytes;
+  return BCHFFT_OK;
+#endif
+}
+
 // ---- per-kernel profiling -------------------------------------------------------------------
 struct ProfRec {
   const char *name;

@@ -70,7 +70,7 @@ static int fft_run(bchfft_field *f, DeviceBuffer &ws, const uint32_t *d_polys, s
         // XOR-only pass: eight planes per CTA (see k_ty_pass)
         const size_t smem8 = ((size_t)4 * 8) << pd.t;
         BCHFFT_ENSURE_SMEM(k_ty_pass<PS>, f->device, smem8);
-        grid.z = PS / 8;
+        grid.x *= PS / 8;
         BCHFFT_RUN(k_ty_pass<PS>, grid, dim3(nt_ty), smem8, stream, pdst, dst_words, pd);
         continue;
       }

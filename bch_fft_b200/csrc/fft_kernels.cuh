@@ -300,11 +300,12 @@ __device__ __forceinline__ void tile_taylor_dispatch(uint32_t *S, uint32_t T, ui
 // same depth, lo and local bit both descending by one, at most five levels (a six-bit group
 // that reaches into the five lowest local bits cannot be made bank-conflict free by the
 // swizzle: those stay at four)
-__device__ __forceinline__ uint32_t taylor_run(const PassDesc &desc, const TileGeom &g, uint32_t i)
+__device__ __forceinline__ uint32_t taylor_run(const PassDesc &desc, const TileGeom &g, uint32_t i,
+                                               uint32_t max_levels = 5u)
 {
   const PassOp op = desc.ops[i];
   uint32_t c = 1;
-  while (c < 5 && i + c < desc.nops) {
+  while (c < max_levels && i + c < desc.nops) {
     const PassOp nx = desc.ops[i + c];
     if (nx.type != OP_TY || nx.d != op.d || nx.lo + c != op.lo ||
         g.local_bit(nx.lo) + c != g.local_bit(op.lo))
@@ -467,17 +468,18 @@ k_gm_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t s
 // ---- Taylor-only pass on a group of planes --------------------------------------------------
 // A pass that contains only Taylor levels (XOR only, plane-wise) does not need whole elements:
 // each CTA takes MP = 8 of the PS plane words of every position of the tile (one 32-byte
-// sector), so its tile is half the size and two or three CTAs are resident per SM -- the
-// load / sweep / store phases of neighbouring CTAs overlap.  grid = (tiles, slabs, PS / 8).
+// sector), so its tile is half the size and three CTAs are resident per SM -- the load / sweep /
+// store phases of neighbouring CTAs overlap.  grid = (tiles * PS/8, slabs): the plane groups of
+// one tile are adjacent CTAs, so they run together and share the 64-byte DRAM bursts.
 template <int PSW>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, BCHFFT_MINB_TY)
 k_ty_pass(uint32_t *__restrict__ buf, size_t slab_words, PassDesc desc)
 {
-  constexpr int MP = 8;
+  constexpr int MP = 8, NG = PSW / 8;
   BCHFFT_DYN_SMEM(uint32_t, S);
   const uint32_t T = 1u << desc.t;
-  const TileGeom g = tile_geom(desc, blockIdx.x);
-  uint32_t *base = buf + (size_t)blockIdx.y * slab_words + blockIdx.z * MP;
+  const TileGeom g = tile_geom(desc, blockIdx.x / NG);
+  uint32_t *base = buf + (size_t)blockIdx.y * slab_words + (blockIdx.x % NG) * MP;
   constexpr int U = 4;
   for (uint32_t b0 = threadIdx.x; b0 < T; b0 += U * blockDim.x) {
     uint4 q[U][2];
@@ -509,7 +511,7 @@ k_ty_pass(uint32_t *__restrict__ buf, size_t slab_words, PassDesc desc)
   __syncthreads();
   uint32_t i = 0;
   while (i < desc.nops) {
-    const uint32_t c = taylor_run(desc, g, i);
+    const uint32_t c = taylor_run(desc, g, i, BCHFFT_TY_LEVELS);
     const uint32_t g0 = g.local_bit(desc.ops[i].lo) + 1u - c;
     tile_taylor_dispatch(S, T, desc.t, g0, c, (uint32_t)MP);
     i += c;

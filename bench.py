@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--fft-batch", type=int, default=4096, help="polynomials per GPU (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extras", action="store_true",
+                    help="also time BASELINE configs[3] (additive FFT GF(2^20), 256 polynomials) and "
+                         "configs[4] (multiplicative FFT GF(2^16)) device-resident")
     return ap.parse_args()
 
 
@@ -351,6 +354,10 @@ def run_ours(args, rank, world, local_rank):
         fft = run_fft(args, rank, world, local_rank, lib, host, peak_gbs, peak_src, barrier,
                       max_over_ranks, torch, api, _lib)
 
+    extras = None
+    if args.extras:
+        extras = run_extras(args, rank, world, local_rank, lib, host, barrier, max_over_ranks, torch, api)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "codewords/s", "n_gpus": world,
@@ -358,7 +365,7 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic", "config": config_dict(args), "gpu_launches": int(launches),
             "clocks": clocks.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
-            "parity": parity, "decode_stats": stats, "fft": fft,
+            "parity": parity, "decode_stats": stats, "fft": fft, "extras": extras,
         }
         print(json.dumps(line), flush=True)
 
@@ -447,6 +454,47 @@ def run_fft(args, rank, world, local_rank, lib, host, peak_gbs, peak_src, barrie
                        "m": m, "batch_per_gpu": Bf, "io": "u32 coefficients in, u32 evaluations out "
                        "(reference ABI)", "l2": "inputs and outputs (2 x 1 GiB) exceed the L2"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "parity": parity}
+
+
+def run_extras(args, rank, world, local_rank, lib, host, barrier, max_over_ranks, torch, api):
+    """device-resident timings of the two remaining BASELINE configs (no e2e / CPU legs)"""
+    dev = torch.device("cuda", local_rank)
+    out = {}
+    stream = torch.cuda.Stream(device=dev)
+    for name, m, B, mult in (("additive_fft_gf2_20", 20, 256, False), ("multiplicative_fft_gf2_16", 16, 512, True)):
+        n = 1 << m
+        field = host.create_binary_finite_field(m)
+        dfield = api.DeviceField(field, local_rank)
+        polys = synth.random_polys(m, B, 0xC4 + rank)
+        with torch.cuda.stream(stream):
+            d_in = torch.from_numpy(polys.view(np.int32)).to(dev)
+            d_out = torch.empty_like(d_in)
+            sp = stream.cuda_stream
+
+            def step():
+                if mult:
+                    dfield.multiplicative_fft_dev(d_in.data_ptr(), d_out.data_ptr(), n - 1, B, sp)
+                else:
+                    dfield.additive_fft_dev(d_in.data_ptr(), d_out.data_ptr(), n - 1, B, sp)
+
+            for _ in range(2):
+                step()
+            barrier()
+            steps = max(1, min(args.steps, 3))
+            evs = []
+            for _ in range(steps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                step()
+                b.record(stream)
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            total_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+        out[name] = {"value": world * B * n * steps / (total_ms * 1e-3), "unit": "points/s",
+                     "ms_per_step": total_ms / steps, "m": m, "batch_per_gpu": B}
+        dfield.close()
+        del d_in, d_out
+    return out
 
 
 def main():
