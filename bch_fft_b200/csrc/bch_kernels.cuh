@@ -23,14 +23,15 @@ constexpr int kSynSub = 256;  // positions per LFSR work item
 //
 // grid = (position chunks, slabs); chunk = `chunk_pos` positions (multiple of kSynSub, <= the
 // shared-memory plane buffer); acc: [slab][nodd][M] plane words, zero-initialised, XOR-merged;
-// parity: [slab] plane word = XOR of all codeword bits (c(1), the reference's FFT-path
-// syndrome[0]).
+// parity: [slab] plane word = syndrome[0] of the reference: XOR of the codeword bits selected by
+// `vbits` -- all ones on the reference's FFT path (c(1)), the bits (X^i mod g)(1) on its direct
+// path, where it evaluates the remainder r = c mod g at 1 (bch.c:258-262, 301-314).
 template <int M>
 __global__ void __launch_bounds__(BCHFFT_NT_SYN, BCHFFT_MINB_SYN)
 k_syndrome(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32_t length_bits,
            uint32_t batch, uint32_t chunk_pos, uint32_t nodd, const uint32_t *__restrict__ taps,
-           const uint32_t *__restrict__ fold, uint32_t nsub_total, uint32_t *__restrict__ acc,
-           uint32_t *__restrict__ parity)
+           const uint32_t *__restrict__ fold, uint32_t nsub_total, const uint32_t *__restrict__ vbits,
+           uint32_t *__restrict__ acc, uint32_t *__restrict__ parity)
 {
   BCHFFT_DYN_SMEM(uint32_t, smem);
   const uint32_t slab = blockIdx.y;
@@ -65,10 +66,11 @@ k_syndrome(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32
       for (int l = 0; l < 32; ++l) x[l] &= mask;
     }
     transpose32(x);
+    const uint32_t vw = (w < words32_per_cw) ? vbits[w] : 0u;
 #pragma unroll
     for (int b = 0; b < 32; ++b) {
       planes[g * 33u + b] = x[b];
-      par ^= x[b];
+      par ^= x[b] & (0u - ((vw >> b) & 1u));
     }
   }
   if (par) atomicXor(&s_par, par);
@@ -115,12 +117,11 @@ k_syndrome(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32
 }
 
 // One thread per codeword: syndromes[cw][0..d-1] (u32), flag[cw] (bch.c:317-324).
-// syndrome[0] follows the reference's method rule: parity of the word when the reference would
-// take its FFT path (bch.c:240-254), else 0 (value for every valid codeword on its direct path;
-// it never changes the decode result).
+// syndrome[0] (not a BCH syndrome; method dependent in the reference, see k_syndrome) comes from
+// the parity word.
 template <int M>
 __global__ void k_syn_finish(const uint32_t *__restrict__ acc, const uint32_t *__restrict__ parity,
-                             uint32_t nodd, uint32_t d, uint32_t batch, uint32_t fft_rule,
+                             uint32_t nodd, uint32_t d, uint32_t batch,
                              uint32_t *__restrict__ syn, int32_t *__restrict__ flag)
 {
   const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,7 +129,7 @@ __global__ void k_syn_finish(const uint32_t *__restrict__ acc, const uint32_t *_
   const uint32_t slab = cw >> 5, l = cw & 31u;
   uint32_t *s = syn + (size_t)cw * d;
   uint32_t any = 0u;
-  s[0] = fft_rule ? ((parity[slab] >> l) & 1u) : 0u;
+  s[0] = (parity[slab] >> l) & 1u;
   any |= s[0];
   for (uint32_t i = 1; i < d; ++i) {
     uint32_t v;

@@ -12,7 +12,7 @@ struct bchfft_code {
   uint32_t nodd = 0;         // odd syndromes computed directly: S_1, S_3, .., S_{2 nodd - 1}
   uint32_t syn_fft_rule = 0; // reference would take its FFT syndrome path (bch.c:240-254)
   uint32_t chunk_pos = 0, nchunks = 0, nsub_total = 0;
-  uint32_t *d_taps = nullptr, *d_fold = nullptr;
+  uint32_t *d_taps = nullptr, *d_fold = nullptr, *d_vbits = nullptr;
   // work sets: [0] serves the device-pointer and stage-level entry points, [1] .. [3] are the
   // lanes of the pipelined host entry point (copy-in / decode / copy-out overlap)
   struct WorkSet {
@@ -120,10 +120,10 @@ static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, 
   BCHFFT_RUN(k_syndrome<M>, dim3(c->nchunks, ns), dim3(kNtSyn), smem, st,
                 (const uint32_t *)d_words, c->wpc * 2u, c->length, (uint32_t)cnt, c->chunk_pos,
                 c->nodd, (const uint32_t *)c->d_taps, (const uint32_t *)c->d_fold, c->nsub_total,
-                s.acc, s.parity);
+                (const uint32_t *)c->d_vbits, s.acc, s.parity);
   BCHFFT_RUN(k_syn_finish<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
                 (const uint32_t *)s.acc, (const uint32_t *)s.parity, c->nodd, c->d, (uint32_t)cnt,
-                c->syn_fft_rule, s.syn, s.flag);
+                s.syn, s.flag);
   return BCHFFT_OK;
 }
 
@@ -279,7 +279,6 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
     set_error("bchfft_code_create: need odd distance >= 3 and distance < length <= 2^m");
     return BCHFFT_ERR_ARG;
   }
-  (void)packed_gen_poly;  // the decoder only needs the roots x^1..x^(d-1), not g itself
   BCHFFT_CUDA_TRY(cudaSetDevice(f->device));
   bchfft_code *c = new bchfft_code();
   c->f = f;
@@ -323,7 +322,35 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
         fold[((size_t)ji * c->nsub_total + qg) * M + b] = f->h_exp[e];
       }
   }
-  cudaError_t e1 = cudaMalloc((void **)&c->d_taps, taps.size() * 4 + 16);
+  // syndrome[0] selector bits (see k_syndrome): all ones when the reference evaluates c at 1
+  // (FFT path), (X^i mod g)(1) when it evaluates the remainder c mod g at 1 (direct path)
+  std::vector<uint32_t> vbits(c->wpc * 2u, 0u);
+  if (c->syn_fft_rule || !packed_gen_poly) {
+    for (uint32_t i = 0; i < length; i++) vbits[i >> 5] |= 1u << (i & 31u);
+  } else {
+    const uint32_t gd = gen_poly_degree, gw = gd / 64u + 1u;
+    std::vector<uint64_t> r(gw + 1, 0ull);   // r = X^i mod g, starts at 1
+    r[0] = 1ull;
+    uint32_t par = 1u;
+    for (uint32_t i = 0; i < length; i++) {
+      if (par) vbits[i >> 5] |= 1u << (i & 31u);
+      // r <- r * X mod g
+      uint64_t carry = 0;
+      for (uint32_t k = 0; k < gw; k++) {
+        const uint64_t nc = r[k] >> 63;
+        r[k] = (r[k] << 1) | carry;
+        carry = nc;
+      }
+      if ((r[gd >> 6] >> (gd & 63u)) & 1ull)
+        for (uint32_t k = 0; k < gw; k++) r[k] ^= packed_gen_poly[k];
+      par = 0u;
+      for (uint32_t k = 0; k < gw; k++) par ^= (uint32_t)__builtin_popcountll(r[k]);
+      par &= 1u;
+    }
+  }
+  cudaError_t e0 = cudaMalloc((void **)&c->d_vbits, vbits.size() * 4 + 16);
+  if (e0 == cudaSuccess) cudaMemcpy(c->d_vbits, vbits.data(), vbits.size() * 4, cudaMemcpyHostToDevice);
+  cudaError_t e1 = (e0 != cudaSuccess) ? e0 : cudaMalloc((void **)&c->d_taps, taps.size() * 4 + 16);
   cudaError_t e2 = cudaMalloc((void **)&c->d_fold, fold.size() * 4 + 16);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     set_error("bchfft_code_create: cudaMalloc failed");
@@ -343,6 +370,7 @@ extern "C" void bchfft_code_destroy(bchfft_code *c)
   cudaStreamSynchronize(c->f->stream);
   cudaFree(c->d_taps);
   cudaFree(c->d_fold);
+  cudaFree(c->d_vbits);
   for (auto &w : c->work) {
     w.scratch.release();
     w.fwd_buf.release();

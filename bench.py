@@ -56,6 +56,18 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(kernel, units_per_launch):
+    """DRAM bytes per launch of `kernel` = bytes per unit measured by ncu (dram__bytes_read.sum +
+    dram__bytes_write.sum, profiles/traffic.json, produced by tools/ncu_summary.py's input) x the
+    units this launch processes; None when no capture exists for the kernel"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            ent = json.load(f).get(kernel)
+        return ent["dram_bytes_per_unit"] * units_per_launch if ent else None
+    except Exception:
+        return None
+
+
 def make_decode_input(code, length, t, batch, seed):
     bits = (synth.splitmix64(seed, 64 * code.data_bits) & np.uint64(1)).astype(np.uint32)
     pool = np.stack([code.encode(b) for b in bits.reshape(64, -1)])
@@ -286,12 +298,7 @@ def run_ours(args, rank, world, local_rank):
     top_ms, top_n = prof[top]
     per_launch_units = B / top_n
     achieved = per_launch_units * CW_BYTES_8191 / (top_ms / top_n * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(top)
-    except Exception:
-        pass
+    traffic = measured_traffic(top, per_launch_units)
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_codeword": CW_BYTES_8191,
@@ -412,8 +419,8 @@ def run_fft(args, rank, world, local_rank, lib, host, peak_gbs, peak_src, barrie
     points_per_launch = Bf * n / passes
     achieved = points_per_launch * bytes_per_point / (top_ms / top_n * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_point": bytes_per_point, "points_per_launch": points_per_launch,
+                "frac": achieved / peak_gbs, "traffic": measured_traffic(top, points_per_launch),
+                "peak_source": peak_src, "algorithmic_bytes_per_point": bytes_per_point, "points_per_launch": points_per_launch,
                 "launch_ms": top_ms / top_n,
                 "kernel_share_of_step": {k: round(v[0] / ksum, 4) for k, v in prof.items()},
                 "whole_step_frac": (Bf * n * bytes_per_point / (total_ms / args.steps * 1e-3) / 1e9) / peak_gbs}
