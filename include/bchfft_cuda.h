@@ -98,8 +98,8 @@ int bchfft_bch_decode_dev(bchfft_code *c, uint64_t *d_words, size_t batch, uint8
 
 /* Stage-level entry points, for callers that drive the stages one by one like bch/main.c:103-122.
  * syndromes: [batch][distance] = c(x^i), i = 0..d-1 (bch_eval_syndrome, bch.c:228-326; entry 0
- * follows the reference's method rule: parity of the word on its FFT path, 0-for-codewords on
- * its direct path); flags[i] = its return value. */
+ * follows the reference's method rule: c(1) on its FFT path, (c mod g)(1) on its direct path);
+ * flags[i] = its return value. */
 int bchfft_bch_syndrome_host(bchfft_code *c, const uint64_t *words, size_t batch,
                              uint32_t *syndromes, int32_t *flags);
 /* bch_compute_elp (bch.c:328-404): elp: [batch][distance+1] (C[0..L], zero-initialised

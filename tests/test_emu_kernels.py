@@ -219,3 +219,51 @@ def test_emu_multiplicative_fft_unknown_factorisation(emu_libs):
     f = host.create_binary_finite_field(5)
     data = np.arange(32, dtype=np.uint32)
     assert f.multiplicative_FFT(data) == 1          # multiplicative_fft.c:110-114
+
+
+def test_emu_edge_cases_and_errors(emu_libs, port):
+    """empty and one-item batches, argument errors, unsupported field degrees (C-ABI contract)"""
+    cabi, host = emu_libs
+    h = _field(cabi, port, 8)
+    n = 256
+    polys = np.arange(n, dtype=np.uint32)[None, :].copy()
+    res = np.full((1, n), 7, np.uint32)
+    # empty batch: ok, nothing written
+    assert cabi.bchfft_additive_fft_host(h, polys.ctypes.data, n, res.ctypes.data, n, None, n, n - 1, 0) == 0
+    assert (res == 7).all()
+    # null / short-stride arguments are rejected with a message
+    assert cabi.bchfft_additive_fft_host(h, None, n, res.ctypes.data, n, None, n, n - 1, 1) < 0
+    assert cabi.bchfft_additive_fft_dev(h, polys.ctypes.data, n - 1, res.ctypes.data, n, None, n, n - 1, 1, None) < 0
+    assert b"stride" in cabi.bchfft_last_error()
+    # one item
+    assert cabi.bchfft_additive_fft_host(h, polys.ctypes.data, n, res.ctypes.data, n, None, n, n - 1, 1) == 0
+    assert (res[0, : n - 1] == port.additive_fft(8, polys[0], n - 1)[0]).all()
+    # field tables that are not the reference's are refused
+    exp, log = port.tables(8)
+    bad = exp.copy()
+    bad[8] ^= 2
+    hh = C.c_void_p()
+    assert cabi.bchfft_field_create(0, 8, bad.ctypes.data, log.ctypes.data, C.byref(hh)) < 0
+    e26 = np.zeros(4, np.uint32)
+    assert cabi.bchfft_field_create(0, 26, e26.ctypes.data, e26.ctypes.data, C.byref(hh)) == -3
+    # code creation argument checks (bch.c:37: distance >= length is no code)
+    c = C.c_void_p()
+    assert cabi.bchfft_code_create(h, 255, 255, None, 0, C.byref(c)) < 0
+    assert cabi.bchfft_code_create(h, 4, 255, None, 0, C.byref(c)) < 0          # even distance
+    pc = port.code(255, 8)
+    assert cabi.bchfft_code_create(h, 17, 255, pc.gen.ctypes.data, pc.gen_degree, C.byref(c)) == 0
+    words = np.zeros((1, pc.words), np.uint64)
+    ok = np.zeros(1, np.uint8)
+    corr = np.full(1, 9, np.uint32)
+    assert cabi.bchfft_bch_decode_host(c, words.ctypes.data, 0, ok.ctypes.data, corr.ctypes.data) == 0
+    assert corr[0] == 9
+    flip(words[0], 200)
+    assert cabi.bchfft_bch_decode_host(c, words.ctypes.data, 1, ok.ctypes.data, corr.ctypes.data) == 0
+    assert ok[0] == 1 and corr[0] == 1 and not words.any()
+    cabi.bchfft_code_destroy(c)
+    cabi.bchfft_field_destroy(h)
+    # host API: the reference's failure conventions
+    with pytest.raises(ValueError):
+        host.bch_gen_code(255, 255)                       # m_packed_gen_poly == NULL
+    with pytest.raises(ValueError):
+        host.create_binary_finite_field(31)               # exp == log == NULL

@@ -1,0 +1,55 @@
+"""Host-side planning logic (bch_fft_b200/csrc/gm_plan.h), compiled with g++ and exercised on
+the CPU: evaluation basis (Cantor chain), position permutation, pass schedule invariants."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def plan_dump(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("plan") / "plan_dump")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "bch_fft_b200", "csrc"),
+                    os.path.join(ROOT, "tools", "plan_dump.cpp"), "-o", exe], check=True)
+    return exe
+
+
+def run(exe, m, K, t):
+    out = subprocess.run([exe, str(m), str(K), str(t)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    head = dict(kv.split("=") for kv in out.stdout.splitlines()[0].split())
+    passes = [dict(kv.split("=") for kv in l.split()[1:]) for l in out.stdout.splitlines()[1:]]
+    return {k: int(v) for k, v in head.items()}, passes
+
+
+@pytest.mark.parametrize("m,chain", [(8, 8), (12, 4), (13, 1), (16, 16), (20, 4), (10, 2), (7, 1)])
+def test_cantor_chain_length(plan_dump, m, chain):
+    """twist-free depths = 2^a for m = 2^a * odd"""
+    head, _ = run(plan_dump, m, m, 11)
+    assert head["twist_free_depths"] == chain and head["perm_ok"] == 1
+    assert head["tw_ops"] == m - chain and head["bf_ops"] == m
+    assert head["ty_ops"] == m * (m - 1) // 2
+
+
+@pytest.mark.parametrize("m,K,t", [(16, 16, 11), (20, 20, 11), (13, 13, 12), (13, 5, 11), (16, 10, 11),
+                                   (10, 10, 4), (8, 3, 2), (20, 7, 11)])
+def test_pass_schedule_invariants(plan_dump, m, K, t):
+    head, passes = run(plan_dump, m, K, t)
+    assert passes
+    nops = 0
+    for p in passes:
+        dom, tt, window = int(p["dom"]), int(p["t"]), int(p["window"], 16)
+        assert tt == min(t, dom) and bin(window).count("1") == tt and window < (1 << max(dom, 1))
+        # the window is at most two runs of bits
+        assert len(re.findall(r"1+", bin(window)[2:])) <= 2
+        nops += int(p["ops"])
+    assert nops == head["tw_ops"] + head["ty_ops"] + head["bf_ops"]
+    assert head["bf_ops"] == K
+
+
+def test_gf2_16_is_nine_passes(plan_dump):
+    head, passes = run(plan_dump, 16, 16, 11)
+    assert head["passes"] == 9 and head["tw_ops"] == 0
