@@ -38,6 +38,13 @@
 #ifndef BCHFFT_TY_LEVELS
 #define BCHFFT_TY_LEVELS 4
 #endif
+// one-plane Taylor passes of the plane-major path: tile bits and resident CTAs per SM
+#ifndef BCHFFT_PLANE_T
+#define BCHFFT_PLANE_T 14
+#endif
+#ifndef BCHFFT_MINB_PLANE
+#define BCHFFT_MINB_PLANE 2
+#endif
 #ifndef BCHFFT_NT_LOC
 #define BCHFFT_NT_LOC 256
 #endif

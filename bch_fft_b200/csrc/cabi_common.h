@@ -76,6 +76,8 @@ struct bchfft_field {
   uint32_t twist_free = 0;               // depths whose twist is the identity (gm_plan.h)
   bchfft::FftTables tab;
   std::map<int, bchfft::GmPlan> plans;   // keyed by K
+  bchfft::GmPlanPM pm_plan;              // plane-major schedule (fully twist-free fields)
+  bool pm_checked = false, pm_ok = false;
   bchfft::DeviceBuffer ws;               // slab workspace
   bchfft::DeviceBuffer stage_in, stage_out, stage_aux;  // device staging for the _host variants
   // two lanes of the pipelined additive-FFT host entry point (copy-in / transform / copy-out overlap)

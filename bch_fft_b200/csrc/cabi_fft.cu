@@ -10,6 +10,63 @@ static int ceil_log2(uint32_t x)
   return k;
 }
 
+// Plane-major schedule (gm_plan_pm): bitslice into [slab][plane][position], XOR-only one-plane
+// passes, butterfly passes on whole-element tiles, the last of which writes the element-major
+// buffer the output gather reads.
+template <int M>
+static int fft_run_pm(bchfft_field *f, DeviceBuffer &ws, const uint32_t *d_polys, size_t poly_stride,
+                      uint32_t *d_results, size_t result_stride, uint32_t *d_natural, size_t natural_stride,
+                      uint32_t ncoef, size_t batch, cudaStream_t stream)
+{
+  constexpr int PS = plane_stride(M);
+  const uint32_t n = f->n;
+  const GmPlanPM &plan = f->pm_plan;
+  const size_t slab_words = (size_t)n * PS;
+  const size_t nslabs = (batch + 31) / 32;
+  size_t chunk = f->chunk_bytes / (2 * slab_words * sizeof(uint32_t));
+  if (chunk < 1) chunk = 1;
+  if (chunk > nslabs) chunk = nslabs;
+  if (chunk > 65535) chunk = 65535;
+  int rc = ws.reserve(chunk * 2 * slab_words * sizeof(uint32_t));
+  if (rc) return rc;
+  uint32_t *bufA = (uint32_t *)ws.p, *bufB = bufA + chunk * slab_words;
+#ifdef BCHFFT_EMU
+  const int nt_pass = 32, nt_plane = 32;
+#else
+  const int nt_pass = BCHFFT_NT_PASS, nt_plane = 256;
+#endif
+  for (size_t s0 = 0; s0 < nslabs; s0 += chunk) {
+    const size_t cs = (nslabs - s0 < chunk) ? nslabs - s0 : chunk;
+    const uint32_t items = (uint32_t)((batch - s0 * 32 < cs * 32) ? batch - s0 * 32 : cs * 32);
+    BCHFFT_RUN(k_bitslice_in<M>, dim3((n + 127) / 128, (unsigned)cs), dim3(128), 0, stream,
+               d_polys + s0 * 32 * poly_stride, poly_stride, items, ncoef, (uint32_t)M, bufA, 1u);
+    for (const PassDesc &pd : plan.plane_passes) {
+      const size_t smem = (size_t)4 << pd.t;
+      BCHFFT_ENSURE_SMEM(k_ty_plane_pass<1>, f->device, smem);
+      BCHFFT_RUN(k_ty_plane_pass<1>, dim3(1u << (pd.dom_bits - pd.t), M, (unsigned)cs), dim3(nt_plane), smem,
+                 stream, bufA, (uint32_t)M, (uint32_t)PS, pd);
+    }
+    for (size_t pi = 0; pi < plan.bf_passes.size(); pi++) {
+      const PassDesc &pd = plan.bf_passes[pi];
+      const bool last = pi + 1 == plan.bf_passes.size();
+      const size_t smem = ((size_t)4 * M) << pd.t;
+      BCHFFT_ENSURE_SMEM(k_gm_pass_pm<M>, f->device, smem);
+      BCHFFT_RUN(k_gm_pass_pm<M>, dim3(1u << (pd.dom_bits - pd.t), (unsigned)cs), dim3(nt_pass), smem, stream,
+                 (const uint32_t *)bufA, last ? bufB : bufA, slab_words, (uint32_t)M, last ? 1u : 0u,
+                 f->tab, pd);
+    }
+    if (d_results)
+      BCHFFT_RUN(k_gather_out<M>, dim3((n - 1u + 127) / 128, (unsigned)cs), dim3(128), 0, stream,
+                 (const uint32_t *)bufB, slab_words, (const uint32_t *)f->d_perm_exp, n - 1u,
+                 d_results + s0 * 32 * result_stride, result_stride, items);
+    if (d_natural)
+      BCHFFT_RUN(k_gather_out<M>, dim3((n + 127) / 128, (unsigned)cs), dim3(128), 0, stream,
+                 (const uint32_t *)bufB, slab_words, (const uint32_t *)f->d_perm_nat, n,
+                 d_natural + s0 * 32 * natural_stride, natural_stride, items);
+  }
+  return BCHFFT_OK;
+}
+
 template <int M>
 static int fft_run(bchfft_field *f, DeviceBuffer &ws, const uint32_t *d_polys, size_t poly_stride, uint32_t *d_results,
                    size_t result_stride, uint32_t *d_natural, size_t natural_stride,
@@ -24,6 +81,17 @@ static int fft_run(bchfft_field *f, DeviceBuffer &ws, const uint32_t *d_polys, s
   if (it == f->plans.end()) it = f->plans.emplace(K, gm_plan(M, K, f->t_max, f->twist_free)).first;
   const GmPlan &plan = it->second;
 
+  // fully twist-free field, full-degree input, transform larger than a tile: plane-major path
+  if (K == M && M > f->t_max && !getenv("BCHFFT_NO_PM")) {
+    if (!f->pm_checked) {
+      const char *pt = getenv("BCHFFT_PLANE_T");
+      f->pm_ok = gm_plan_pm(M, pt ? atoi(pt) : BCHFFT_PLANE_T, f->t_max, f->twist_free, f->pm_plan);
+      f->pm_checked = true;
+    }
+    if (f->pm_ok)
+      return fft_run_pm<M>(f, ws, d_polys, poly_stride, d_results, result_stride, d_natural, natural_stride,
+                           ncoef, batch, stream);
+  }
   const size_t fwd_words = ((size_t)1 << K) * PS;            // per slab
   const size_t bwd_words = (size_t)n * PS;
   const bool separate = K < M;                                // broadcast needs a second buffer

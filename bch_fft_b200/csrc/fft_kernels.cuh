@@ -43,9 +43,12 @@ struct FftTables {
 // ---- AoS u32 -> bitsliced slabs -----------------------------------------------------------
 // src: [batch][item_stride] u32 (the reference ABI's coefficient arrays); coefficient index
 // >= ncoef is read as zero (degree masking of additive_fft.c:99: coefficients 0..p_num_terms).
+// plane_major = 1: dst is [slab][plane][position] (see k_ty_plane_pass) instead of
+// [slab][position][PS].
 template <int M>
 __global__ void k_bitslice_in(const uint32_t *__restrict__ src, size_t item_stride, uint32_t batch,
-                              uint32_t ncoef, uint32_t npos_bits, uint32_t *__restrict__ dst)
+                              uint32_t ncoef, uint32_t npos_bits, uint32_t *__restrict__ dst,
+                              uint32_t plane_major = 0u)
 {
   constexpr int PS = plane_stride(M);
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,6 +61,12 @@ __global__ void k_bitslice_in(const uint32_t *__restrict__ src, size_t item_stri
     x[l] = (item < batch && p < ncoef) ? src[(size_t)item * item_stride + p] : 0u;
   }
   transpose32(x);
+  if (plane_major) {
+    uint32_t *row = dst + ((((size_t)slab * PS) << npos_bits) + p);
+#pragma unroll
+    for (int b = 0; b < M; ++b) row[(size_t)b << npos_bits] = x[b];
+    return;
+  }
   uint4 *out = reinterpret_cast<uint4 *>(dst + ((((size_t)slab) << npos_bits) + p) * PS);
 #pragma unroll
   for (int v = 0; v < PS / 4; ++v) {
@@ -523,6 +532,92 @@ k_ty_pass(uint32_t *__restrict__ buf, size_t slab_words, PassDesc desc)
     out[0] = make_uint4(S[0 * T + sl], S[1 * T + sl], S[2 * T + sl], S[3 * T + sl]);
     out[1] = make_uint4(S[4 * T + sl], S[5 * T + sl], S[6 * T + sl], S[7 * T + sl]);
   }
+}
+
+// ---- plane-major path (fully twist-free fields, e.g. GF(2^16); see gm_plan_pm) ----------------
+// Slab layout [slab][plane][position].  k_ty_plane_pass: one plane of one slab per CTA, tile of
+// 2^t1 positions, Taylor levels only.  grid = (tiles, M, slabs), dynamic smem = 4 * 2^t1 bytes.
+template <int PLANES_PER_CTA>   // always 1 (a template so the header can be included everywhere)
+__global__ void __launch_bounds__(256, BCHFFT_MINB_PLANE)
+k_ty_plane_pass(uint32_t *__restrict__ buf, uint32_t nbits, uint32_t ps, PassDesc desc)
+{
+  BCHFFT_DYN_SMEM(uint32_t, S);
+  const uint32_t T = 1u << desc.t;
+  const TileGeom g = tile_geom(desc, blockIdx.x);
+  uint32_t *row = buf + (((size_t)blockIdx.z * ps + blockIdx.y) << nbits);
+  constexpr int U = 8;
+  for (uint32_t b0 = threadIdx.x; b0 < T; b0 += U * blockDim.x) {
+    uint32_t q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t l = b0 + u * blockDim.x;
+      if (l < T) q[u] = row[g.pos(l)];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t l = b0 + u * blockDim.x;
+      if (l < T) S[swz(l)] = q[u];
+    }
+  }
+  __syncthreads();
+  uint32_t i = 0;
+  while (i < desc.nops) {
+    const uint32_t c = taylor_run(desc, g, i, 5u);
+    const uint32_t g0 = g.local_bit(desc.ops[i].lo) + 1u - c;
+    tile_taylor_dispatch(S, T, desc.t, g0, c, 1u);
+    i += c;
+    __syncthreads();
+  }
+  for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) row[g.pos(l)] = S[swz(l)];
+}
+
+// whole-element tile <-> plane-major slab (lanes run along positions: 128-byte row segments when
+// the window contains the low position bits)
+template <int M>
+__device__ __forceinline__ void tile_load_pm(uint32_t *S, uint32_t t, const uint32_t *__restrict__ src,
+                                             uint32_t nbits, const TileGeom &g)
+{
+  const uint32_t T = 1u << t;
+  constexpr int U = 8;
+  for (uint32_t b0 = threadIdx.x; b0 < M * T; b0 += U * blockDim.x) {
+    uint32_t q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t idx = b0 + u * blockDim.x;
+      if (idx < M * T) q[u] = src[((size_t)(idx >> t) << nbits) + g.pos(idx & (T - 1u))];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t idx = b0 + u * blockDim.x;
+      if (idx < M * T) S[(idx >> t) * T + swz(idx & (T - 1u))] = q[u];
+    }
+  }
+}
+
+template <int M>
+__device__ __forceinline__ void tile_store_pm(const uint32_t *S, uint32_t t, uint32_t *__restrict__ dst,
+                                              uint32_t nbits, const TileGeom &g)
+{
+  const uint32_t T = 1u << t;
+  for (uint32_t idx = threadIdx.x; idx < M * T; idx += blockDim.x)
+    dst[((size_t)(idx >> t) << nbits) + g.pos(idx & (T - 1u))] = S[(idx >> t) * T + swz(idx & (T - 1u))];
+}
+
+// butterfly pass reading the plane-major layout; writes it back in place, or (dst_em = 1) writes
+// the element-major layout k_gather_out reads.  grid = (tiles, slabs).
+template <int M>
+__global__ void __launch_bounds__(BCHFFT_NT_PASS, BCHFFT_MINB_PASS)
+k_gm_pass_pm(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t slab_words,
+             uint32_t nbits, uint32_t dst_em, FftTables tab, PassDesc desc)
+{
+  BCHFFT_DYN_SMEM(uint32_t, S);
+  const uint32_t T = 1u << desc.t;
+  const TileGeom g = tile_geom(desc, blockIdx.x);
+  tile_load_pm<M>(S, desc.t, src + (size_t)blockIdx.y * slab_words, nbits, g);
+  __syncthreads();
+  tile_run_ops<M>(S, T, desc.t, g, tab, desc);
+  if (dst_em) tile_store<M>(S, T, dst + (size_t)blockIdx.y * slab_words, g);
+  else tile_store_pm<M>(S, desc.t, dst + (size_t)blockIdx.y * slab_words, nbits, g);
 }
 
 // ---- bitsliced slabs -> AoS u32, through a position permutation ---------------------------

@@ -242,6 +242,43 @@ struct GmPlan {
   int first_backward;
 };
 
+struct PlanItem {
+  PassOp op;
+  uint32_t bits;
+};
+
+// Greedy packing of an op stream into passes: a pass takes ops while the union of their position
+// bits (plus `required`, bits every window must contain) still fits t bits in at most two runs.
+inline void build_passes(std::vector<PassDesc> &out, const std::vector<PlanItem> &stream, int dom,
+                         int t_max, bool backward, uint32_t src_mask_first, uint32_t required = 0u)
+{
+  size_t i = 0;
+  bool first = true;
+  const int t = t_max < dom ? t_max : dom;
+  do {
+    PassDesc p;
+    memset(&p, 0, sizeof p);
+    uint32_t w = required;
+    while (i < stream.size() && p.nops < (uint32_t)kMaxOps) {
+      const uint32_t cand = w | stream[i].bits;
+      if (__builtin_popcount(cand) > t || bit_runs(cand) > 2) break;
+      w = cand;
+      p.ops[p.nops++] = stream[i].op;
+      i++;
+    }
+    if (dom > 0) {
+      if (w == 0) w = 1u;
+      w = pad_window(w, t, dom);
+      set_window(p, w);
+    }
+    p.dom_bits = dom;
+    p.backward = backward ? 1u : 0u;
+    p.src_mask = (first && backward) ? src_mask_first : 0xFFFFFFFFu;
+    first = false;
+    out.push_back(p);
+  } while (i < stream.size());
+}
+
 // t_max: largest tile (log2 positions) that fits the CTA's shared memory for this M.
 inline GmPlan gm_plan(int m, int K, int t_max, uint32_t twist_free = 0u)
 {
@@ -249,37 +286,7 @@ inline GmPlan gm_plan(int m, int K, int t_max, uint32_t twist_free = 0u)
   plan.m = m;
   plan.K = K;
   plan.t = t_max;
-  struct Item { PassOp op; uint32_t bits; };
-  auto build = [&](const std::vector<Item> &stream, int dom, bool backward, uint32_t src_mask_first) {
-    size_t i = 0;
-    bool first = true;
-    const int t = t_max < dom ? t_max : dom;
-    do {
-      PassDesc p;
-      memset(&p, 0, sizeof p);
-      uint32_t w = 0;
-      while (i < stream.size() && p.nops < (uint32_t)kMaxOps) {
-        const uint32_t cand = w | stream[i].bits;
-        if (__builtin_popcount(cand) > t || bit_runs(cand) > 2) break;
-        w = cand;
-        p.ops[p.nops++] = stream[i].op;
-        i++;
-      }
-      if (dom > 0) {
-        if (w == 0) w = 1u;
-        w = pad_window(w, t, dom);
-        set_window(p, w);
-      } else {
-        p.a0 = p.n0 = p.a1 = p.n1 = p.t = 0;
-      }
-      p.dom_bits = dom;
-      p.backward = backward ? 1u : 0u;
-      p.src_mask = (first && backward) ? src_mask_first : 0xFFFFFFFFu;
-      first = false;
-      plan.passes.push_back(p);
-    } while (i < stream.size());
-  };
-  std::vector<Item> fwd, bwd;
+  std::vector<PlanItem> fwd, bwd;
   for (int d = 0; d < K; d++) {
     if (!((twist_free >> d) & 1u)) fwd.push_back({{OP_TW, (uint8_t)d, 0, 0}, 0u});
     for (int lo = K - 2; lo >= d; lo--) fwd.push_back({{OP_TY, (uint8_t)d, (uint8_t)lo, 0}, 3u << lo});
@@ -289,16 +296,38 @@ inline GmPlan gm_plan(int m, int K, int t_max, uint32_t twist_free = 0u)
     // full-degree input: forward and backward phases work in place on the same buffer, so they
     // form one op stream (the last forward ops and the first butterflies usually share a pass;
     // a transform that fits one tile is a single pass)
-    std::vector<Item> all = fwd;
+    std::vector<PlanItem> all = fwd;
     all.insert(all.end(), bwd.begin(), bwd.end());
     plan.first_backward = 0;
-    build(all, m, true, 0xFFFFFFFFu);
+    build_passes(plan.passes, all, m, t_max, true, 0xFFFFFFFFu);
     return plan;
   }
-  if (!fwd.empty()) build(fwd, K, false, 0xFFFFFFFFu);   // K = 0: constant polynomial, nothing to do
+  if (!fwd.empty()) build_passes(plan.passes, fwd, K, t_max, false, 0xFFFFFFFFu);   // K = 0: constant polynomial
   plan.first_backward = (int)plan.passes.size();
-  build(bwd, m, true, K < m ? ((1u << K) - 1u) : 0xFFFFFFFFu);
+  build_passes(plan.passes, bwd, m, t_max, true, K < m ? ((1u << K) - 1u) : 0xFFFFFFFFu);
   return plan;
+}
+
+// Plane-major schedule for fully twist-free fields (m a power of two, e.g. GF(2^16)), full-degree
+// input.  The forward phase is XOR-only and plane-wise, so it runs on a plane-major slab layout
+// [slab][plane][position] with one-plane tiles of 2^t1 positions (t1 = 14: 64 KB, two CTAs per SM): 3 passes
+// instead of 7 at m = 16.  The butterfly passes read the same layout with whole-element tiles of
+// 2^t2 positions whose windows always contain position bits 0..2 (32-byte runs per plane row);
+// the last one writes the element-major layout the output gather reads.
+struct GmPlanPM {
+  std::vector<PassDesc> plane_passes, bf_passes;
+};
+
+inline bool gm_plan_pm(int m, int t1, int t2, uint32_t twist_free, GmPlanPM &out)
+{
+  if (m <= t2 || m > 24 || t2 < 6 || t1 < 4 || (twist_free & ((1u << m) - 1u)) != ((1u << m) - 1u)) return false;
+  std::vector<PlanItem> fwd, bwd;
+  for (int d = 0; d < m; d++)
+    for (int lo = m - 2; lo >= d; lo--) fwd.push_back({{OP_TY, (uint8_t)d, (uint8_t)lo, 0}, 3u << lo});
+  for (int d = m - 1; d >= 0; d--) bwd.push_back({{OP_BF, (uint8_t)d, 0, 0}, 1u << d});
+  build_passes(out.plane_passes, fwd, m, t1, true, 0xFFFFFFFFu);
+  build_passes(out.bf_passes, bwd, m, t2, true, 0xFFFFFFFFu, 7u);
+  return true;
 }
 
 }  // namespace bchfft
