@@ -107,11 +107,12 @@ __device__ __forceinline__ TileGeom tile_geom(const PassDesc &d, uint32_t tile)
   return g;
 }
 
-// Shared-memory tiles are XOR-swizzled: local position l lives at word l ^ ((l >> 5) & 31) of its
-// plane, i.e. bank = l[4:0] ^ l[9:5].  A warp whose lanes differ in five local bits that hit the
-// five bank bits independently (one of {i, i+5} for each i) is conflict-free, whichever bits the
-// threads themselves iterate over.
-__device__ __forceinline__ uint32_t swz(uint32_t l) { return l ^ ((l >> 5) & 31u); }
+// Shared-memory tiles are XOR-swizzled: local position l lives at word
+// l ^ l[9:5] ^ l[14:10] of its plane, i.e. bank = l[4:0] ^ l[9:5] ^ l[14:10].  A warp whose lanes
+// differ in five local bits with distinct residues mod 5 is conflict-free, whichever bits the
+// threads themselves iterate over.  The map is XOR-linear: swz(a | b) = swz(a) ^ swz(b) for
+// disjoint a, b, so a thread that owns a group of bits adds per-element constants to one base.
+__device__ __forceinline__ uint32_t swz(uint32_t l) { return l ^ ((l >> 5) & 31u) ^ ((l >> 10) & 31u); }
 
 // Enumeration of the 2^(t-r) work items of a sweep in which every thread owns the 2^r positions
 // spanned by local bits [g0, g0+r).  Item bits 0..4 (the lanes of a warp) go to local bit i, or
@@ -157,6 +158,78 @@ __device__ __forceinline__ SweepMap make_sweep_map(uint32_t t, uint32_t g0, uint
     m.start[k] = s;
     m.len[k] = n;
     free_rest &= ~(((1u << n) - 1u) << s);
+    k++;
+  }
+  return m;
+}
+
+// General form of SweepMap (any group position, tiles up to 2^15; used by the OP_TX register
+// sweeps).  Item bits 0..4 (the lanes of a warp) go to five free local
+// bits with distinct residues mod 5 (bit i, else i+5, else i+10), so that the swizzle spreads them
+// over all 32 banks; the remaining item bits fill the other free bits in ascending order.
+struct SweepMapX {
+  uint32_t lane_bit[5];
+  uint32_t start[8], len[8];
+  uint32_t simple, g0, r;
+  __device__ __forceinline__ uint32_t lane_part(uint32_t lane) const
+  {
+    uint32_t l = 0u;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) l |= ((lane >> j) & 1u) << lane_bit[j];
+    return l;
+  }
+  __device__ __forceinline__ uint32_t rest_part(uint32_t rest) const
+  {
+    uint32_t l = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      l |= (rest & ((1u << len[k]) - 1u)) << start[k];
+      rest >>= len[k];
+    }
+    return l;
+  }
+  __device__ __forceinline__ uint32_t pos(uint32_t w) const
+  {
+    if (simple) return ((w >> g0) << (g0 + r)) | (w & ((1u << g0) - 1u));
+    return lane_part(w & 31u) | rest_part(w >> 5);
+  }
+};
+
+__device__ __forceinline__ SweepMapX make_sweep_map_x(uint32_t t, uint32_t g0, uint32_t r)
+{
+  SweepMapX m;
+  m.g0 = g0;
+  m.r = r;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m.start[k] = m.len[k] = 0u;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) m.lane_bit[j] = 0u;
+  m.simple = (t < 10u || g0 >= 5u || r == 0u) ? 1u : 0u;
+  if (m.simple) return m;
+  const uint32_t group = ((1u << r) - 1u) << g0;
+  uint32_t free_bits = ((1u << t) - 1u) & ~group;
+  int nl = 0;
+  for (uint32_t q = 0; q < 5u; ++q) {
+    for (uint32_t c = q; c < t; c += 5u)
+      if ((free_bits >> c) & 1u) {
+        m.lane_bit[nl++] = c;
+        free_bits &= ~(1u << c);
+        break;
+      }
+  }
+  while (nl < 5 && free_bits) {   // not enough residues: take what is left (conflicts accepted)
+    const uint32_t c = (uint32_t)__ffs((int)free_bits) - 1u;
+    m.lane_bit[nl++] = c;
+    free_bits &= ~(1u << c);
+  }
+  int k = 0;
+  while (free_bits && k < 8) {
+    const uint32_t s = (uint32_t)__ffs((int)free_bits) - 1u;
+    uint32_t n = 0;
+    while ((free_bits >> (s + n)) & 1u) n++;
+    m.start[k] = s;
+    m.len[k] = n;
+    free_bits &= ~(((1u << n) - 1u) << s);
     k++;
   }
   return m;
@@ -270,11 +343,11 @@ __device__ __forceinline__ void tile_taylor_multi(uint32_t *S, uint32_t T, uint3
   const uint32_t blocks = T >> R;
   for (uint32_t idx = threadIdx.x; idx < blocks * nplanes; idx += blockDim.x) {
     const uint32_t plane = idx / blocks, w = idx - plane * blocks;
-    const uint32_t base = map.pos(w);
+    const uint32_t sb = swz(map.pos(w));
     uint32_t *row = S + plane * T;
     uint32_t x[1 << R];
 #pragma unroll
-    for (int k = 0; k < (1 << R); ++k) x[k] = row[swz(base + ((uint32_t)k << g0))];
+    for (int k = 0; k < (1 << R); ++k) x[k] = row[sb ^ swz((uint32_t)k << g0)];
 #pragma unroll
     for (int lv = R - 2; lv >= 0; --lv) {
 #pragma unroll
@@ -285,8 +358,130 @@ __device__ __forceinline__ void tile_taylor_multi(uint32_t *S, uint32_t T, uint3
         if (((k >> lv) & 3) == 1) x[k] ^= x[k + (1 << lv)];
     }
 #pragma unroll
-    for (int k = 0; k < (1 << R); ++k) row[swz(base + ((uint32_t)k << g0))] = x[k];
+    for (int k = 0; k < (1 << R); ++k) row[sb ^ swz((uint32_t)k << g0)] = x[k];
   }
+}
+
+// ---- generalised Taylor levels (OP_TX, see gm_plan.h) ---------------------------------------
+// One level, any base: every thread takes targets B_i[off], i = 1 .. t-1, of a super-block; the
+// thread that owns B_1[off] also does B_t[off] ^= B_(2t-1)[off] first (B_t is read by nobody
+// else), so the level needs no barrier of its own.  L = local bit of the block size, h = log2 t.
+static __device__ __noinline__ void tile_tx_generic(uint32_t *S, uint32_t T, uint32_t L, uint32_t h,
+                                                uint32_t nplanes)
+{
+  const uint32_t half = T >> 1;                 // candidate targets per plane: blocks 0 .. t-1
+  const uint32_t tm1 = (1u << h) - 1u;
+  const uint32_t off = tm1 << L, lowmask = (1u << (L + h)) - 1u;
+  for (uint32_t idx = threadIdx.x; idx < half * nplanes; idx += blockDim.x) {
+    const uint32_t plane = idx / half, w = idx - plane * half;
+    const uint32_t blk = (w >> L) & tm1;
+    if (blk == 0u) continue;
+    const uint32_t l = ((w & ~lowmask) << 1) | (w & lowmask);   // zero at the top bit of the block index
+    uint32_t *row = S + plane * T;
+    uint32_t src = row[swz(l + off)];
+    if (blk == 1u) {
+      // l + off lies in B_t; its own source B_(2t-1) is another t-1 blocks up
+      src ^= row[swz(l + 2u * off)];
+      row[swz(l + off)] = src;
+    }
+    row[swz(l)] ^= src;
+  }
+}
+
+// compile-time level on a register block indexed by R local bits: REL = block-size bit relative to
+// the group, H = log2 t.  Descending order makes B_t final before B_1 reads it.
+template <int R, int REL, int H>
+__device__ __forceinline__ void tx_level_regs(uint32_t (&x)[1 << R])
+{
+  constexpr int t = 1 << H;
+  static_assert(REL + H + 1 <= R, "level does not fit the register block");
+#pragma unroll
+  for (int k = (1 << R) - 1; k >= 0; --k) {
+    const int blk = (k >> REL) & (2 * t - 1);
+    if (blk >= 1 && blk <= t) x[k] ^= x[k + ((t - 1) << REL)];
+  }
+}
+
+// Register-resident sweeps over the level sequences the Cantor conversion produces:
+//   TXP_C4   (R = 4)  TX(b+1,2) TX(b,2) TX(b,1) TX(b+2,1)            = whole conversion of 4 bits
+//   TXP_X16  (R = 6)  TX(b+1,4) TX(b,4)                              two levels of base y^16 + y
+//   TXP_X16C (R = 6)  TX(b+1,4) TX(b,4) followed by TXP_C4 at b      (last two levels + low conversion)
+enum { TXP_C4 = 0, TXP_X16 = 1, TXP_X16C = 2 };
+
+template <int PROG, int G0>
+__device__ __noinline__ void tile_tx_regs_at(uint32_t *S, uint32_t T, uint32_t t, uint32_t nplanes)
+{
+  constexpr int R = (PROG == TXP_C4) ? 4 : 6;
+  const SweepMapX map = make_sweep_map_x(t, (uint32_t)G0, R);
+  const uint32_t blocks = T >> R;
+  for (uint32_t idx = threadIdx.x; idx < blocks * nplanes; idx += blockDim.x) {
+    const uint32_t plane = idx / blocks, w = idx - plane * blocks;
+    const uint32_t sb = swz(map.pos(w));
+    uint32_t *row = S + plane * T;
+    uint32_t x[1 << R];
+    // G0 is a compile-time constant: the per-element swizzle constants are immediates
+#pragma unroll
+    for (int k = 0; k < (1 << R); ++k) x[k] = row[sb ^ swz((uint32_t)k << G0)];
+    if constexpr (PROG == TXP_X16 || PROG == TXP_X16C) {
+      tx_level_regs<R, 1, 4>(x);
+      tx_level_regs<R, 0, 4>(x);
+    }
+    if constexpr (PROG == TXP_C4 || PROG == TXP_X16C) {
+      tx_level_regs<R, 1, 2>(x);
+      tx_level_regs<R, 0, 2>(x);
+      tx_level_regs<R, 0, 1>(x);
+      tx_level_regs<R, 2, 1>(x);
+    }
+#pragma unroll
+    for (int k = 0; k < (1 << R); ++k) row[sb ^ swz((uint32_t)k << G0)] = x[k];
+  }
+}
+
+// group positions 0 .. 11 cover every window of tiles up to 2^15 positions (R <= 6 bits above g0)
+template <int PROG>
+__device__ __forceinline__ bool tile_tx_regs(uint32_t *S, uint32_t T, uint32_t t, uint32_t g0, uint32_t nplanes)
+{
+  switch (g0) {
+    case 0: tile_tx_regs_at<PROG, 0>(S, T, t, nplanes); return true;
+    case 1: tile_tx_regs_at<PROG, 1>(S, T, t, nplanes); return true;
+    case 2: tile_tx_regs_at<PROG, 2>(S, T, t, nplanes); return true;
+    case 3: tile_tx_regs_at<PROG, 3>(S, T, t, nplanes); return true;
+    case 4: tile_tx_regs_at<PROG, 4>(S, T, t, nplanes); return true;
+    case 5: tile_tx_regs_at<PROG, 5>(S, T, t, nplanes); return true;
+    case 6: tile_tx_regs_at<PROG, 6>(S, T, t, nplanes); return true;
+    case 7: tile_tx_regs_at<PROG, 7>(S, T, t, nplanes); return true;
+    case 8: tile_tx_regs_at<PROG, 8>(S, T, t, nplanes); return true;
+    case 9: tile_tx_regs_at<PROG, 9>(S, T, t, nplanes); return true;
+    case 10: tile_tx_regs_at<PROG, 10>(S, T, t, nplanes); return true;
+    case 11: tile_tx_regs_at<PROG, 11>(S, T, t, nplanes); return true;
+    default: return false;
+  }
+}
+
+// Runs the OP_TX ops starting at op i that form one sweep; returns how many ops it consumed.
+// Every sweep ends with the data in shared memory; the caller puts the barrier.
+__device__ __forceinline__ uint32_t tile_tx_sweep(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
+                                                  const PassDesc &desc, uint32_t i, uint32_t nplanes)
+{
+  const PassOp op = desc.ops[i];
+  auto is_tx = [&](uint32_t k, uint32_t lo, uint32_t h) -> bool {
+    return k < desc.nops && desc.ops[k].type == OP_TX && desc.ops[k].lo == lo && desc.ops[k].d == h;
+  };
+  auto is_c4 = [&](uint32_t k, uint32_t b) -> bool {
+    return is_tx(k, b + 1u, 2u) && is_tx(k + 1u, b, 2u) && is_tx(k + 2u, b, 1u) && is_tx(k + 3u, b + 2u, 1u);
+  };
+  if (op.d == 4u && op.lo >= 1u && t >= 6u && is_tx(i + 1u, op.lo - 1u, 4u)) {
+    const uint32_t b = op.lo - 1u;
+    if (is_c4(i + 2u, b)) {
+      if (tile_tx_regs<TXP_X16C>(S, T, t, g.local_bit(b), nplanes)) return 6u;
+    } else if (tile_tx_regs<TXP_X16>(S, T, t, g.local_bit(b), nplanes)) {
+      return 2u;
+    }
+  } else if (op.d == 2u && op.lo >= 1u && t >= 4u && is_c4(i, op.lo - 1u)) {
+    if (tile_tx_regs<TXP_C4>(S, T, t, g.local_bit(op.lo - 1u), nplanes)) return 4u;
+  }
+  tile_tx_generic(S, T, g.local_bit(op.lo), op.d, nplanes);
+  return 1u;
 }
 
 // Epilogue hook of the last butterfly sweep of a pass: instead of writing the final values back
@@ -417,7 +612,7 @@ __device__ __forceinline__ void tile_butterfly_r4(uint32_t *S, uint32_t T, uint3
 // Runs the ops of a pass on a tile.  Consecutive Taylor levels of one depth on adjacent bits are
 // fused five at a time, consecutive butterfly levels two at a time (register-resident radix
 // blocks): fewer shared-memory round trips and barriers than one sweep per level.
-template <int M, class Epi = NoEpilogue>
+template <int M, class Epi = NoEpilogue, bool WITH_TX = false>
 __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
                                              const FftTables &tab, const PassDesc &desc,
                                              const Epi *epi = nullptr)
@@ -434,6 +629,8 @@ __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t
       const uint32_t g0 = g.local_bit(op.lo) + 1u - c;   // local bit of the last level's lo
       tile_taylor_dispatch(S, T, t, g0, c, (uint32_t)M);
       i += c;
+    } else if (WITH_TX && op.type == OP_TX) {
+      if constexpr (WITH_TX) i += tile_tx_sweep(S, T, t, g, desc, i, (uint32_t)M);
     } else {
       bool pair = false;
       if (M <= 16 && i + 1 < desc.nops) {
@@ -536,7 +733,7 @@ k_ty_pass(uint32_t *__restrict__ buf, size_t slab_words, PassDesc desc)
 
 // ---- plane-major path (fully twist-free fields, e.g. GF(2^16); see gm_plan_pm) ----------------
 // Slab layout [slab][plane][position].  k_ty_plane_pass: one plane of one slab per CTA, tile of
-// 2^t1 positions, Taylor levels only.  grid = (tiles, M, slabs), dynamic smem = 4 * 2^t1 bytes.
+// 2^t1 positions, XOR-only levels (OP_TX / OP_TY).  grid = (tiles, M, slabs), dynamic smem = 4 * 2^t1 bytes.
 template <int PLANES_PER_CTA>   // always 1 (a template so the header can be included everywhere)
 __global__ void __launch_bounds__(256, BCHFFT_MINB_PLANE)
 k_ty_plane_pass(uint32_t *__restrict__ buf, uint32_t nbits, uint32_t ps, PassDesc desc)
@@ -562,10 +759,14 @@ k_ty_plane_pass(uint32_t *__restrict__ buf, uint32_t nbits, uint32_t ps, PassDes
   __syncthreads();
   uint32_t i = 0;
   while (i < desc.nops) {
-    const uint32_t c = taylor_run(desc, g, i, 5u);
-    const uint32_t g0 = g.local_bit(desc.ops[i].lo) + 1u - c;
-    tile_taylor_dispatch(S, T, desc.t, g0, c, 1u);
-    i += c;
+    if (desc.ops[i].type == OP_TX) {
+      i += tile_tx_sweep(S, T, desc.t, g, desc, i, 1u);
+    } else {
+      const uint32_t c = taylor_run(desc, g, i, 5u);
+      const uint32_t g0 = g.local_bit(desc.ops[i].lo) + 1u - c;
+      tile_taylor_dispatch(S, T, desc.t, g0, c, 1u);
+      i += c;
+    }
     __syncthreads();
   }
   for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) row[g.pos(l)] = S[swz(l)];
@@ -615,7 +816,7 @@ k_gm_pass_pm(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_
   const TileGeom g = tile_geom(desc, blockIdx.x);
   tile_load_pm<M>(S, desc.t, src + (size_t)blockIdx.y * slab_words, nbits, g);
   __syncthreads();
-  tile_run_ops<M>(S, T, desc.t, g, tab, desc);
+  tile_run_ops<M, NoEpilogue, true>(S, T, desc.t, g, tab, desc);
   if (dst_em) tile_store<M>(S, T, dst + (size_t)blockIdx.y * slab_words, g);
   else tile_store_pm<M>(S, desc.t, dst + (size_t)blockIdx.y * slab_words, nbits, g);
 }

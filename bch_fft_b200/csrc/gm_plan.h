@@ -21,7 +21,11 @@
 
 namespace bchfft {
 
-enum : uint8_t { OP_TW = 0, OP_TY = 1, OP_BF = 2 };
+// OP_TX(lo, h) (h stored in PassOp::d): one level of the generalised Taylor expansion at
+// y^(2^h) + y (Gao-Mateer, base t = 2^h): blocks B_0 .. B_(2t-1) of 2^lo positions inside every
+// super-block of 2^(lo+h+1) positions; B_t ^= B_(2t-1), then B_i ^= B_(i+t-1) for i = 1 .. t-1.
+// OP_TX(lo, 1) is OP_TY on bits (lo+1, lo).
+enum : uint8_t { OP_TW = 0, OP_TY = 1, OP_BF = 2, OP_TX = 3 };
 
 struct PassOp {
   uint8_t type, d, lo, pad;
@@ -309,23 +313,60 @@ inline GmPlan gm_plan(int m, int K, int t_max, uint32_t twist_free = 0u)
 }
 
 // Plane-major schedule for fully twist-free fields (m a power of two, e.g. GF(2^16)), full-degree
-// input.  The forward phase is XOR-only and plane-wise, so it runs on a plane-major slab layout
-// [slab][plane][position] with one-plane tiles of 2^t1 positions (t1 = 14: 64 KB, two CTAs per SM): 3 passes
-// instead of 7 at m = 16.  The butterfly passes read the same layout with whole-element tiles of
-// 2^t2 positions whose windows always contain position bits 0..2 (32-byte runs per plane row);
-// the last one writes the element-major layout the output gather reads.
+// input.
+//
+// Forward phase.  With every twist equal to one the forward phase is the change of basis from
+// monomials to the products prod_d s_d(x)^(p_d) of the Cantor subspace polynomials
+// s_0 = x, s_(d+1) = s_d^2 + s_d.  Because s_(2^k)(x) = x^(2^(2^k)) + x, that conversion splits
+// recursively (Lin, Al-Naffouri, Han, Chung 2016, basis conversion for Cantor bases): for a
+// window of w = 2h index bits starting at bit b0, expand in base y^(2^h) + y (h levels OP_TX(b0+k, h),
+// k = h-1 .. 0), then convert the low and the high h bits independently.  m/2 * log2(m) levels
+// instead of the m(m-1)/2 Taylor levels of the plain recursion: 32 instead of 120 at m = 16
+// (tools/gm_model.py checks that both give the same coefficients).
+//
+// The phase is XOR-only and plane-wise, so it runs on a plane-major slab layout
+// [slab][plane][position] with one-plane tiles of 2^t1 positions.  Every window contains position
+// bits 0..2 (32-byte runs per plane row).  The butterfly passes read the same layout with
+// whole-element tiles of 2^t2 positions; a trailing forward pass whose ops fit the first butterfly
+// window is folded into it, and the last butterfly pass writes the element-major layout the output
+// gather reads.
 struct GmPlanPM {
   std::vector<PassDesc> plane_passes, bf_passes;
 };
 
+inline void cantor_conversion_ops(std::vector<PlanItem> &out, int b0, int w)
+{
+  if (w < 2) return;
+  const int h = w / 2;
+  for (int k = h - 1; k >= 0; k--)
+    out.push_back({{OP_TX, (uint8_t)h, (uint8_t)(b0 + k), 0}, ((2u << h) - 1u) << (b0 + k)});
+  cantor_conversion_ops(out, b0, h);
+  cantor_conversion_ops(out, b0 + h, h);
+}
+
 inline bool gm_plan_pm(int m, int t1, int t2, uint32_t twist_free, GmPlanPM &out)
 {
-  if (m <= t2 || m > 24 || t2 < 6 || t1 < 4 || (twist_free & ((1u << m) - 1u)) != ((1u << m) - 1u)) return false;
+  if (m <= t2 || m > 24 || (m & (m - 1)) || t2 < 6 || t1 < 4 ||
+      (twist_free & ((1u << m) - 1u)) != ((1u << m) - 1u))
+    return false;
   std::vector<PlanItem> fwd, bwd;
-  for (int d = 0; d < m; d++)
-    for (int lo = m - 2; lo >= d; lo--) fwd.push_back({{OP_TY, (uint8_t)d, (uint8_t)lo, 0}, 3u << lo});
+  cantor_conversion_ops(fwd, 0, m);
+  // every level must fit a window next to the required low bits
+  for (const PlanItem &it : fwd)
+    if (__builtin_popcount(it.bits | 7u) > (t1 < m ? t1 : m) || bit_runs(it.bits | 7u) > 2) return false;
+  build_passes(out.plane_passes, fwd, m, t1, true, 0xFFFFFFFFu, 7u);
+  // fold the last forward pass into the first butterfly pass when its bits fit that window
+  if (!out.plane_passes.empty()) {
+    const PassDesc &last = out.plane_passes.back();
+    uint32_t bits = 7u | (1u << (m - 1));
+    for (uint32_t i = 0; i < last.nops; i++) bits |= ((2u << last.ops[i].d) - 1u) << last.ops[i].lo;
+    if (__builtin_popcount(bits) <= t2 && bit_runs(bits) <= 2) {
+      for (uint32_t i = 0; i < last.nops; i++)
+        bwd.push_back({last.ops[i], ((2u << last.ops[i].d) - 1u) << last.ops[i].lo});
+      out.plane_passes.pop_back();
+    }
+  }
   for (int d = m - 1; d >= 0; d--) bwd.push_back({{OP_BF, (uint8_t)d, 0, 0}, 1u << d});
-  build_passes(out.plane_passes, fwd, m, t1, true, 0xFFFFFFFFu);
   build_passes(out.bf_passes, bwd, m, t2, true, 0xFFFFFFFFu, 7u);
   return true;
 }

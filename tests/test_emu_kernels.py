@@ -83,10 +83,27 @@ def test_emu_multi_pass_schedules(port):
         "            assert (res[b, :n-1] == P.additive_fft(m, polys[b], terms)[0]).all(), (m, terms)\n"
         "print('ok')\n")
     emu = os.path.join(ROOT, "bch_fft_b200", "csrc", "libbchfft_emu.so")
-    for tmax in ("2", "3", "4", "6"):
-        env = dict(os.environ, BCHFFT_TMAX=tmax)
+    # BCHFFT_PLANE_T=8 lets GF(2^8) take the plane-major path (Cantor basis conversion) for tmax >= 6
+    for tmax in ("2", "3", "4", "6", "7"):
+        env = dict(os.environ, BCHFFT_TMAX=tmax, BCHFFT_PLANE_T="8")
         out = subprocess.run([sys.executable, "-c", code, emu], env=env, capture_output=True, text=True)
         assert out.returncode == 0 and "ok" in out.stdout, (tmax, out.stderr[-2000:])
+
+
+def test_emu_plane_major_gf2_16(emu_libs, port):
+    """GF(2^16), full degree: plane-major schedule (two one-plane passes of generalised Taylor
+    levels, conversion tail folded into the first butterfly pass) against the oracle"""
+    cabi, _ = emu_libs
+    m, n = 16, 1 << 16
+    h = _field(cabi, port, m)
+    polys = np.random.default_rng(16).integers(0, n, (2, n), dtype=np.uint32)
+    before = cabi.bchfft_launch_count()
+    res, nat = _fft(cabi, h, polys, n - 1)
+    assert cabi.bchfft_launch_count() - before == 7   # bitslice, 2 plane, 2 butterfly, 2 gathers
+    for b in range(2):
+        o, c = port.additive_fft(m, polys[b], n - 1)
+        assert (res[b] == o).all() and (nat[b] == c).all()
+    cabi.bchfft_field_destroy(h)
 
 
 def _words_for(pc, n, t, B, rng):

@@ -21,8 +21,21 @@ def run(exe, m, K, t):
     out = subprocess.run([exe, str(m), str(K), str(t)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     head = dict(kv.split("=") for kv in out.stdout.splitlines()[0].split())
-    passes = [dict(kv.split("=") for kv in l.split()[1:]) for l in out.stdout.splitlines()[1:]]
+    passes = [dict(kv.split("=") for kv in l.split()[1:]) for l in out.stdout.splitlines()[1:]
+              if not l.startswith("  pm ")]
     return {k: int(v) for k, v in head.items()}, passes
+
+
+def run_pm(exe, m, t2, t1):
+    """plane-major schedule lines: (kind, tile bits, window, [ops])"""
+    out = subprocess.run([exe, str(m), str(m), str(t2), str(t1)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    res = []
+    for l in out.stdout.splitlines():
+        if l.startswith("  pm "):
+            f = l.split()
+            res.append((f[1], int(f[3].split("=")[1]), int(f[4].split("=")[1], 16), f[6:]))
+    return res
 
 
 @pytest.mark.parametrize("m,chain", [(8, 8), (12, 4), (13, 1), (16, 16), (20, 4), (10, 2), (7, 1)])
@@ -53,3 +66,27 @@ def test_pass_schedule_invariants(plan_dump, m, K, t):
 def test_gf2_16_is_nine_passes(plan_dump):
     head, passes = run(plan_dump, 16, 16, 11)
     assert head["passes"] == 9 and head["tw_ops"] == 0
+
+
+def test_plane_major_schedule_gf2_16(plan_dump):
+    """Cantor basis conversion: m/2 * log2(m) = 32 generalised Taylor levels instead of 120, two
+    one-plane passes, the rest folded into the first butterfly pass; every window keeps position
+    bits 0..2 (32-byte runs per plane row)"""
+    pm = run_pm(plan_dump, 16, 11, 14)
+    assert [k for k, *_ in pm] == ["plane", "plane", "bf", "bf"]
+    ops = [o for *_, oo in pm for o in oo]
+    assert sum(o.startswith("TX") for o in ops) == 32 and sum(o.startswith("BF") for o in ops) == 16
+    assert ops[-16:] == [f"BF({d},0)" for d in range(15, -1, -1)]
+    for kind, t, window, oo in pm:
+        assert bin(window).count("1") == t and window & 7 == 7
+        assert len(re.findall(r"1+", bin(window)[2:])) <= 2
+        for o in oo:
+            a, b = (int(x) for x in o[3:-1].split(","))
+            bits = (((2 << b) - 1) << a) if o.startswith("TX") else (1 << a)
+            assert bits & ~window == 0, (o, hex(window))
+
+
+def test_plane_major_needs_a_power_of_two_degree(plan_dump):
+    assert run_pm(plan_dump, 20, 11, 14) == [] and run_pm(plan_dump, 13, 11, 14) == []
+    assert run_pm(plan_dump, 8, 6, 6) == []          # base-16 level + low bits do not fit 6-bit tiles
+    assert [k for k, *_ in run_pm(plan_dump, 8, 6, 8)] == ["plane", "bf", "bf"]

@@ -50,8 +50,61 @@ __device__ __forceinline__ void mad_variant(uint32_t (&acc)[M], const uint32_t (
   bs_reduce<M>(p);
 #pragma unroll
   for (int i = 0; i < M; ++i) acc[i] = p[i];
+#elif MB_VARIANT == 3
+  // warp-uniform constant: branch over the set bits of c, XOR only (no masks)
+  uint32_t p[2 * M - 1];
+#pragma unroll
+  for (int k = 0; k < 2 * M - 1; ++k) p[k] = (k < M) ? acc[k] : 0u;
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    if ((c >> j) & 1u) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) p[i + j] ^= a[i];
+    }
+  }
+  bs_reduce<M>(p);
+#pragma unroll
+  for (int i = 0; i < M; ++i) acc[i] = p[i];
+#elif MB_VARIANT == 4
+  // warp-uniform constant, two bits of c per branch: both set -> one three-input XOR per plane
+  uint32_t p[2 * M];
+#pragma unroll
+  for (int k = 0; k < 2 * M; ++k) p[k] = (k < M) ? acc[k] : 0u;
+#pragma unroll
+  for (int j = 0; j < M; j += 2) {
+    const uint32_t two = (c >> j) & 3u;
+    if (j + 1 == M) {
+      if (two & 1u) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) p[i + j] ^= a[i];
+      }
+    } else if (two == 1u) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) p[i + j] ^= a[i];
+    } else if (two == 2u) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) p[i + j + 1] ^= a[i];
+    } else if (two == 3u) {
+      p[j] ^= a[0];
+#pragma unroll
+      for (int i = 1; i < M; ++i) p[i + j] = xor3(p[i + j], a[i], a[i - 1]);
+      p[j + M] ^= a[M - 1];
+    }
+  }
+  uint32_t q[2 * M - 1];
+#pragma unroll
+  for (int k = 0; k < 2 * M - 1; ++k) q[k] = p[k];
+  bs_reduce<M>(q);
+#pragma unroll
+  for (int i = 0; i < M; ++i) acc[i] = q[i];
 #endif
 }
+
+#if MB_VARIANT >= 3
+#define MB_CONST_INDEX ((blockIdx.x * 37u + (threadIdx.x >> 5)) + it)
+#else
+#define MB_CONST_INDEX (tid + it)
+#endif
 
 __global__ void __launch_bounds__(512, 1) k(uint32_t *out, const uint32_t *consts, int iters)
 {
@@ -63,7 +116,7 @@ __global__ void __launch_bounds__(512, 1) k(uint32_t *out, const uint32_t *const
     a[i] = tid * 40503u + 7 * i + 1;
   }
   for (int it = 0; it < iters; ++it) {
-    const uint32_t c = consts[(tid + it) & 1023];
+    const uint32_t c = consts[MB_CONST_INDEX & 1023];
     mad_variant<MB_M>(acc, a, c);
 #pragma unroll
     for (int i = 0; i < MB_M; ++i) a[i] ^= acc[(i + 1) % MB_M];

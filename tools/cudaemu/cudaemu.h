@@ -26,6 +26,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__
 #define __launch_bounds__(...)
 #define __restrict__ __restrict
 #define __shared__ static

@@ -108,6 +108,44 @@ def gm_fft(F, coef, K=None, consts=None):
     return a
 
 
+def taylor_forward_xor(a, m):
+    """forward phase of a fully twist-free field (XOR only): m(m-1)/2 Taylor levels"""
+    a = a.copy()
+    pos = np.arange(1 << m)
+    for d in range(m):
+        for lo in range(m - 2, d - 1, -1):
+            q = 1 << lo
+            sel = (((pos >> (lo + 1)) & 1) == 1) & (((pos >> lo) & 1) == 0)
+            a[pos[sel]] ^= a[pos[sel] + q]
+            sel = (((pos >> (lo + 1)) & 1) == 0) & (((pos >> lo) & 1) == 1)
+            a[pos[sel]] ^= a[pos[sel] + q]
+    return a
+
+
+def tx_level(a, m, lo, h):
+    """OP_TX(lo, h) of gm_plan.h: generalised Taylor level at y^(2^h) + y, blocks of 2^lo"""
+    t = 1 << h
+    pos = np.arange(1 << m)
+    blk = (pos >> lo) & (2 * t - 1)
+    off = (t - 1) << lo
+    sel = blk == t
+    a[pos[sel]] ^= a[pos[sel] + off]
+    sel = (blk >= 1) & (blk < t)
+    a[pos[sel]] ^= a[pos[sel] + off]
+
+
+def cantor_conversion(a, m, b0=0, w=None):
+    """same coefficients as taylor_forward_xor in (m/2) log2(m) levels (m a power of two)"""
+    w = m if w is None else w
+    if w < 2:
+        return
+    h = w // 2
+    for k in range(h - 1, -1, -1):
+        tx_level(a, m, b0 + k, h)
+    cantor_conversion(a, m, b0, h)
+    cantor_conversion(a, m, b0 + h, h)
+
+
 def natural(F, a):
     out = np.zeros_like(a)
     for p in range(F.n):
@@ -121,6 +159,12 @@ if __name__ == "__main__":
     from oracle.pyoracle import Port
     P = Port()
     rng = np.random.default_rng(3)
+    for m in (2, 4, 8, 16):
+        a = rng.integers(0, 1 << 30, 1 << m)
+        b = a.copy()
+        cantor_conversion(b, m)
+        assert (taylor_forward_xor(a, m) == b).all(), m
+    print("cantor conversion == taylor forward (m = 2, 4, 8, 16)")
     for m in (3, 4, 5, 8, 10, 13):
         F = Field(m)
         c = gm_constants(F)

@@ -47,5 +47,21 @@ int main(int argc, char **argv)
     uint32_t w = (((1u << p.n0) - 1u) << p.a0) | (p.n1 ? (((1u << p.n1) - 1u) << p.a1) : 0u);
     printf("  pass dom=%u t=%u window=0x%x ops=%u backward=%u\n", p.dom_bits, p.t, w, p.nops, p.backward);
   }
+  GmPlanPM pm;
+  const int t1 = argc > 4 ? atoi(argv[4]) : 14;
+  if (K == m && gm_plan_pm(m, t1, t, c.twist_free, pm)) {
+    auto dump = [](const char *name, const std::vector<PassDesc> &v) {
+      for (auto &p : v) {
+        uint32_t w = (((1u << p.n0) - 1u) << p.a0) | (p.n1 ? (((1u << p.n1) - 1u) << p.a1) : 0u);
+        printf("  pm %s pass t=%u window=0x%x ops:", name, p.t, w);
+        for (uint32_t i = 0; i < p.nops; i++)
+          printf(" %s(%u,%u)", p.ops[i].type == OP_TX ? "TX" : p.ops[i].type == OP_BF ? "BF" : "??",
+                 p.ops[i].type == OP_TX ? p.ops[i].lo : p.ops[i].d, p.ops[i].type == OP_TX ? p.ops[i].d : 0u);
+        printf("\n");
+      }
+    };
+    dump("plane", pm.plane_passes);
+    dump("bf", pm.bf_passes);
+  }
   return perm_ok ? 0 : 1;
 }
