@@ -40,6 +40,21 @@ static int fft_run_pm(bchfft_field *f, DeviceBuffer &ws, const uint32_t *d_polys
     const uint32_t items = (uint32_t)((batch - s0 * 32 < cs * 32) ? batch - s0 * 32 : cs * 32);
     BCHFFT_RUN(k_bitslice_in<M>, dim3((n + 127) / 128, (unsigned)cs), dim3(128), 0, stream,
                d_polys + s0 * 32 * poly_stride, poly_stride, items, ncoef, (uint32_t)M, bufA, 1u);
+    for (const PassDesc &pd : plan.line_passes) {
+      // levels lo = kmin+nlev-1 .. kmin of base 2^h straight on the slab
+      const uint32_t nlev = pd.nops, h = pd.ops[0].d, kmin = pd.ops[nlev - 1].lo;
+      const uint32_t u = ((1u << h) - 1u) << kmin;
+      const unsigned per = (u + nt_plane - 1) / nt_plane, nsuper = n >> (kmin + nlev + h);
+      const dim3 grid(per * nsuper, M, (unsigned)cs);
+      switch (nlev) {
+        case 1: BCHFFT_RUN(k_tx_line_pass<1>, grid, dim3(nt_plane), 0, stream, bufA, (uint32_t)M, (uint32_t)PS, kmin, h); break;
+        case 2: BCHFFT_RUN(k_tx_line_pass<2>, grid, dim3(nt_plane), 0, stream, bufA, (uint32_t)M, (uint32_t)PS, kmin, h); break;
+        case 3: BCHFFT_RUN(k_tx_line_pass<3>, grid, dim3(nt_plane), 0, stream, bufA, (uint32_t)M, (uint32_t)PS, kmin, h); break;
+        case 4: BCHFFT_RUN(k_tx_line_pass<4>, grid, dim3(nt_plane), 0, stream, bufA, (uint32_t)M, (uint32_t)PS, kmin, h); break;
+        case 5: BCHFFT_RUN(k_tx_line_pass<5>, grid, dim3(nt_plane), 0, stream, bufA, (uint32_t)M, (uint32_t)PS, kmin, h); break;
+        default: BCHFFT_RUN(k_tx_line_pass<6>, grid, dim3(nt_plane), 0, stream, bufA, (uint32_t)M, (uint32_t)PS, kmin, h); break;
+      }
+    }
     for (const PassDesc &pd : plan.plane_passes) {
       const size_t smem = (size_t)4 << pd.t;
       BCHFFT_ENSURE_SMEM(k_ty_plane_pass<1>, f->device, smem);

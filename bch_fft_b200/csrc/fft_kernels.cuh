@@ -458,6 +458,88 @@ __device__ __forceinline__ bool tile_tx_regs(uint32_t *S, uint32_t T, uint32_t t
   }
 }
 
+// ---- line sweeps: several consecutive levels of one base in registers ------------------------
+// Levels kappa = kmin+NLEV-1 .. kmin of base t = 2^h only ever combine positions that differ by
+// multiples of u = (t-1) 2^kmin, and stay inside super-blocks of 2^(kmin+NLEV+h) positions.  A
+// thread therefore owns the line r + u c, c = 0 .. 2^NLEV (r < u; the last element exists for
+// r < 2^(NLEV+kmin) and is only ever a source), runs all NLEV levels on it in registers and writes
+// it back: two memory accesses per element for the whole group of levels.  Level kappa pairs c
+// with c + 2^(kappa-kmin) where the block index of the target is in [1, t]; descending c makes B_t
+// final before B_1 reads it.  q0 = r >> kmin.
+template <int NLEV>
+__device__ __forceinline__ void tx_line_levels(uint32_t (&x)[(1 << NLEV) + 1], uint32_t q0, uint32_t h)
+{
+  constexpr int NE = (1 << NLEV) + 1;
+  const uint32_t t = 1u << h, tm1 = t - 1u, m2 = 2u * t - 1u;
+#pragma unroll
+  for (int lv = NLEV - 1; lv >= 0; --lv) {
+#pragma unroll
+    for (int c = NE - 1 - (1 << lv); c >= 0; --c) {
+      const uint32_t blk = ((q0 + tm1 * (uint32_t)c) >> lv) & m2;
+      if (blk - 1u < t) x[c] ^= x[c + (1 << lv)];
+    }
+  }
+}
+
+// on a shared-memory tile: L = local bit of kmin
+template <int NLEV>
+__device__ __noinline__ void tile_tx_lines(uint32_t *S, uint32_t T, uint32_t L, uint32_t h, uint32_t nplanes)
+{
+  constexpr int NE = (1 << NLEV) + 1;
+  const uint32_t u = ((1u << h) - 1u) << L;
+  const uint32_t sbits = L + NLEV + h;
+  const uint32_t nsuper = T >> sbits;
+  const uint32_t items = nsuper * u;
+  for (uint32_t idx = threadIdx.x; idx < items * nplanes; idx += blockDim.x) {
+    const uint32_t plane = idx / items, w = idx - plane * items;
+    const uint32_t sb = w / u, r = w - sb * u;
+    uint32_t *row = S + plane * T;
+    const uint32_t l0 = (sb << sbits) + r;
+    const bool last = r < (1u << (NLEV + L));
+    uint32_t x[NE];
+#pragma unroll
+    for (int c = 0; c < NE - 1; ++c) x[c] = row[swz(l0 + u * (uint32_t)c)];
+    x[NE - 1] = last ? row[swz(l0 + u * (uint32_t)(NE - 1))] : 0u;
+    tx_line_levels<NLEV>(x, r >> L, h);
+#pragma unroll
+    for (int c = 0; c < NE - 1; ++c) row[swz(l0 + u * (uint32_t)c)] = x[c];
+  }
+}
+
+__device__ __forceinline__ void tile_tx_lines_dispatch(uint32_t *S, uint32_t T, uint32_t L, uint32_t h,
+                                                       uint32_t nlev, uint32_t nplanes)
+{
+  if (nlev == 6) tile_tx_lines<6>(S, T, L, h, nplanes);
+  else if (nlev == 5) tile_tx_lines<5>(S, T, L, h, nplanes);
+  else if (nlev == 4) tile_tx_lines<4>(S, T, L, h, nplanes);
+  else if (nlev == 3) tile_tx_lines<3>(S, T, L, h, nplanes);
+  else tile_tx_lines<2>(S, T, L, h, nplanes);
+}
+
+// directly on a plane-major slab in HBM (no tile): one kernel pass for levels whose super-block
+// is larger than a tile.  Consecutive threads own consecutive r, so every load / store of a warp is
+// one contiguous row segment.  grid = (ceil(u / threads) * super-blocks per row, planes, slabs).
+template <int NLEV>
+__global__ void __launch_bounds__(256)
+k_tx_line_pass(uint32_t *__restrict__ buf, uint32_t nbits, uint32_t ps, uint32_t kmin, uint32_t h)
+{
+  constexpr int NE = (1 << NLEV) + 1;
+  const uint32_t u = ((1u << h) - 1u) << kmin;
+  const uint32_t sbits = kmin + NLEV + h;
+  const uint32_t per = (u + blockDim.x - 1u) / blockDim.x;
+  const uint32_t sb = blockIdx.x / per, r = (blockIdx.x - sb * per) * blockDim.x + threadIdx.x;
+  if (r >= u) return;
+  uint32_t *row = buf + (((size_t)blockIdx.z * ps + blockIdx.y) << nbits) + ((size_t)sb << sbits) + r;
+  const bool last = r < (1u << (NLEV + kmin));
+  uint32_t x[NE];
+#pragma unroll
+  for (int c = 0; c < NE - 1; ++c) x[c] = row[(size_t)u * c];
+  x[NE - 1] = last ? row[(size_t)u * (NE - 1)] : 0u;
+  tx_line_levels<NLEV>(x, r >> kmin, h);
+#pragma unroll
+  for (int c = 0; c < NE - 1; ++c) row[(size_t)u * c] = x[c];
+}
+
 // Runs the OP_TX ops starting at op i that form one sweep; returns how many ops it consumed.
 // Every sweep ends with the data in shared memory; the caller puts the barrier.
 __device__ __forceinline__ uint32_t tile_tx_sweep(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
@@ -470,6 +552,17 @@ __device__ __forceinline__ uint32_t tile_tx_sweep(uint32_t *S, uint32_t T, uint3
   auto is_c4 = [&](uint32_t k, uint32_t b) -> bool {
     return is_tx(k, b + 1u, 2u) && is_tx(k + 1u, b, 2u) && is_tx(k + 2u, b, 1u) && is_tx(k + 3u, b + 2u, 1u);
   };
+  if (op.d >= 5u) {
+    // run of levels of one large base: line sweep (at most six levels, super-block inside the tile)
+    uint32_t n = 1u;
+    while (n < 6u && op.lo >= n && is_tx(i + n, op.lo - n, op.d) &&
+           g.local_bit(op.lo - n) + n == g.local_bit(op.lo))
+      n++;
+    if (n >= 2u && g.local_bit(op.lo) + op.d + 1u <= t) {
+      tile_tx_lines_dispatch(S, T, g.local_bit(op.lo - (n - 1u)), op.d, n, nplanes);
+      return n;
+    }
+  }
   if (op.d == 4u && op.lo >= 1u && t >= 6u && is_tx(i + 1u, op.lo - 1u, 4u)) {
     const uint32_t b = op.lo - 1u;
     if (is_c4(i + 2u, b)) {

@@ -330,8 +330,12 @@ inline GmPlan gm_plan(int m, int K, int t_max, uint32_t twist_free = 0u)
 // whole-element tiles of 2^t2 positions; a trailing forward pass whose ops fit the first butterfly
 // window is folded into it, and the last butterfly pass writes the element-major layout the output
 // gather reads.
+//
+// Leading levels whose super-block (2^(lo+h+1) positions) is larger than a plane tile run as
+// "line passes" straight on the slab in HBM (k_tx_line_pass: up to six consecutive levels of one
+// base per pass, no tile).
 struct GmPlanPM {
-  std::vector<PassDesc> plane_passes, bf_passes;
+  std::vector<PassDesc> line_passes, plane_passes, bf_passes;
 };
 
 inline void cantor_conversion_ops(std::vector<PlanItem> &out, int b0, int w)
@@ -351,10 +355,30 @@ inline bool gm_plan_pm(int m, int t1, int t2, uint32_t twist_free, GmPlanPM &out
     return false;
   std::vector<PlanItem> fwd, bwd;
   cantor_conversion_ops(fwd, 0, m);
-  // every level must fit a window next to the required low bits
+  {
+    const int tile = t1 < m ? t1 : m;
+    size_t i = 0;
+    while (i < fwd.size() && fwd[i].op.lo + fwd[i].op.d + 1 > tile) {
+      PassDesc p;
+      memset(&p, 0, sizeof p);
+      p.dom_bits = p.t = m;
+      p.n0 = m;
+      p.a1 = m;
+      p.backward = 1u;
+      p.src_mask = 0xFFFFFFFFu;
+      p.ops[p.nops++] = fwd[i].op;
+      i++;
+      while (i < fwd.size() && p.nops < 6u && fwd[i].op.d == p.ops[0].d &&
+             fwd[i].op.lo + p.nops == p.ops[0].lo && fwd[i].op.lo + fwd[i].op.d + 1 > tile)
+        p.ops[p.nops++] = fwd[i++].op;
+      out.line_passes.push_back(p);
+    }
+    fwd.erase(fwd.begin(), fwd.begin() + i);
+  }
+  // every remaining level must fit a window next to the required low bits
   for (const PlanItem &it : fwd)
     if (__builtin_popcount(it.bits | 7u) > (t1 < m ? t1 : m) || bit_runs(it.bits | 7u) > 2) return false;
-  build_passes(out.plane_passes, fwd, m, t1, true, 0xFFFFFFFFu, 7u);
+  if (!fwd.empty()) build_passes(out.plane_passes, fwd, m, t1, true, 0xFFFFFFFFu, 7u);
   // fold the last forward pass into the first butterfly pass when its bits fit that window
   if (!out.plane_passes.empty()) {
     const PassDesc &last = out.plane_passes.back();

@@ -83,9 +83,10 @@ def test_emu_multi_pass_schedules(port):
         "            assert (res[b, :n-1] == P.additive_fft(m, polys[b], terms)[0]).all(), (m, terms)\n"
         "print('ok')\n")
     emu = os.path.join(ROOT, "bch_fft_b200", "csrc", "libbchfft_emu.so")
-    # BCHFFT_PLANE_T=8 lets GF(2^8) take the plane-major path (Cantor basis conversion) for tmax >= 6
-    for tmax in ("2", "3", "4", "6", "7"):
-        env = dict(os.environ, BCHFFT_TMAX=tmax, BCHFFT_PLANE_T="8")
+    # tmax >= 6 lets GF(2^8) take the plane-major path (Cantor basis conversion); BCHFFT_PLANE_T
+    # = 8: one tile pass, 7 / 6: line pass(es) on the slab + tile passes
+    for tmax, plane_t in (("2", "8"), ("3", "8"), ("4", "8"), ("6", "8"), ("7", "8"), ("6", "7"), ("6", "6")):
+        env = dict(os.environ, BCHFFT_TMAX=tmax, BCHFFT_PLANE_T=plane_t)
         out = subprocess.run([sys.executable, "-c", code, emu], env=env, capture_output=True, text=True)
         assert out.returncode == 0 and "ok" in out.stdout, (tmax, out.stderr[-2000:])
 

@@ -69,11 +69,14 @@ def test_gf2_16_is_nine_passes(plan_dump):
 
 
 def test_plane_major_schedule_gf2_16(plan_dump):
-    """Cantor basis conversion: m/2 * log2(m) = 32 generalised Taylor levels instead of 120, two
-    one-plane passes, the rest folded into the first butterfly pass; every window keeps position
-    bits 0..2 (32-byte runs per plane row)"""
+    """Cantor basis conversion: m/2 * log2(m) = 32 generalised Taylor levels instead of 120: one
+    line pass (levels whose super-block exceeds a tile), one one-plane tile pass, the rest folded
+    into the first butterfly pass; every tile window keeps position bits 0..2 (32-byte runs per
+    plane row)"""
     pm = run_pm(plan_dump, 16, 11, 14)
-    assert [k for k, *_ in pm] == ["plane", "plane", "bf", "bf"]
+    assert [k for k, *_ in pm] == ["line", "plane", "bf", "bf"]
+    assert pm[0][3] == ["TX(7,8)", "TX(6,8)"]
+    assert [k for k, *_ in run_pm(plan_dump, 16, 11, 13)] == ["line", "plane", "bf", "bf"]
     ops = [o for *_, oo in pm for o in oo]
     assert sum(o.startswith("TX") for o in ops) == 32 and sum(o.startswith("BF") for o in ops) == 16
     assert ops[-16:] == [f"BF({d},0)" for d in range(15, -1, -1)]
@@ -88,5 +91,5 @@ def test_plane_major_schedule_gf2_16(plan_dump):
 
 def test_plane_major_needs_a_power_of_two_degree(plan_dump):
     assert run_pm(plan_dump, 20, 11, 14) == [] and run_pm(plan_dump, 13, 11, 14) == []
-    assert run_pm(plan_dump, 8, 6, 6) == []          # base-16 level + low bits do not fit 6-bit tiles
     assert [k for k, *_ in run_pm(plan_dump, 8, 6, 8)] == ["plane", "bf", "bf"]
+    assert [k for k, *_ in run_pm(plan_dump, 8, 6, 6)] == ["line", "plane", "plane", "plane", "bf", "bf"]

@@ -60,6 +60,7 @@ int main(int argc, char **argv)
         printf("\n");
       }
     };
+    dump("line", pm.line_passes);
     dump("plane", pm.plane_passes);
     dump("bf", pm.bf_passes);
   }
