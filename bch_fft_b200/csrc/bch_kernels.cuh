@@ -394,6 +394,244 @@ k_locate(const uint32_t *__restrict__ F, const uint32_t *__restrict__ counts,
   tile_run_ops<M, RootEpilogue<M>>(S, T, bwd.t, g, tab, bwd, &epi);
 }
 
+
+// ---- root search, low locator degrees (K <= 5): warp lanes = 32 slabs -------------------------
+// The butterfly multipliers depend on the position only.  When the 32 lanes of a warp hold 32
+// different slabs at the SAME positions, every multiplier is warp-uniform and the multiply
+// branches over its set bits instead of masking all M*M partial products (bs_mad_uniform).  A
+// "group" is 32 slabs of one bucket (1024 codewords); its forward values are stored
+// [group][coefficient 2^kmax][plane M][lane 32].  A CTA takes a range of 32-position tiles of one
+// group; per tile the K levels run as radix-4 / radix-2 steps, one block per warp, through a
+// [32 positions][M planes][32 lanes] shared-memory buffer (first step reads the forward values,
+// last step feeds the zero test).
+constexpr int kLocUMaxK = 5;
+
+// F2 index of (group, coefficient i, plane b, lane)
+__device__ __forceinline__ size_t f2_index(uint32_t group, uint32_t kmax, uint32_t i, uint32_t M_, uint32_t b,
+                                           uint32_t lane)
+{
+  return ((((size_t)group << kmax) + i) * M_ + b) * 32u + lane;
+}
+
+// forward phase like k_elp_fwd, output in the group layout.  grid as k_elp_fwd.
+template <int M>
+__global__ void __launch_bounds__(256)
+k_elp_fwd_u(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin, uint32_t d,
+            const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists, uint32_t batch,
+            uint32_t sb, uint32_t kmax, FftTables tab, PassDesc fwd, uint32_t *__restrict__ F2)
+{
+  BCHFFT_DYN_SMEM(uint32_t, S);
+  const uint32_t K = fwd.dom_bits, TK = 1u << K, tt = K + sb, T = 1u << tt;
+  const uint32_t pop = counts[K], nslabs = (pop + 31u) >> 5;
+  const uint32_t slab0 = blockIdx.x << sb;
+  if (slab0 >= nslabs) return;
+  uint32_t gbase = 0u;
+  for (uint32_t k = 1; k < K; ++k) gbase += (((counts[k] + 31u) >> 5) + 31u) >> 5;
+  const uint32_t *list = lists + (size_t)K * batch;
+  for (uint32_t idx = threadIdx.x; idx < T; idx += blockDim.x) {
+    const uint32_t slab = slab0 + (idx >> K), i = idx & (TK - 1u);
+    uint32_t x[32];
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const uint32_t at = slab * 32u + l;
+      uint32_t v = 0u;
+      if (at < pop) {
+        const uint32_t cw = list[at];
+        if (i <= Lin[cw]) v = elp[(size_t)cw * (d + 1) + i];
+      }
+      x[l] = v;
+    }
+    transpose32(x);
+    const uint32_t sl = swz(idx);
+#pragma unroll
+    for (int b = 0; b < M; ++b) S[b * T + sl] = x[b];
+  }
+  __syncthreads();
+  TileGeom g;
+  g.fixed = 0u;
+  g.a0 = 0u;
+  g.n0 = tt;
+  g.a1 = tt;
+  g.mask0 = T - 1u;
+  g.pmask = TK - 1u;
+  tile_run_ops<M>(S, T, tt, g, tab, fwd);
+  for (uint32_t idx = threadIdx.x; idx < T; idx += blockDim.x) {
+    const uint32_t slab = slab0 + (idx >> K), i = idx & (TK - 1u);
+    if (slab >= nslabs) continue;
+    const uint32_t sl = swz(idx);
+#pragma unroll
+    for (int b = 0; b < M; ++b) F2[f2_index(gbase + (slab >> 5), kmax, i, M, b, slab & 31u)] = S[b * T + sl];
+  }
+}
+
+template <int M>
+struct LocU {
+  // per-thread view of the job
+  const uint32_t *F2g;        // forward values of this group (+ lane)
+  uint32_t *W;                // shared buffer (+ lane)
+  const uint32_t *gam;
+  const uint32_t *gam_off;
+  const uint32_t *errloc;
+  const uint32_t *list;       // codeword indices of this lane's slab
+  uint32_t *count, *positions;
+  uint32_t active, pos_stride, kmask, tile0;
+
+  __device__ __forceinline__ void load(uint32_t (&e)[M], uint32_t p, bool from_f) const
+  {
+    if (from_f) {
+      const uint32_t *src = F2g + (size_t)(p & kmask) * M * 32u;
+#pragma unroll
+      for (int b = 0; b < M; ++b) e[b] = src[b * 32];
+    } else {
+#pragma unroll
+      for (int b = 0; b < M; ++b) e[b] = W[(p * M + b) * 32u];
+    }
+  }
+  __device__ __forceinline__ void store(const uint32_t (&e)[M], uint32_t p) const
+  {
+#pragma unroll
+    for (int b = 0; b < M; ++b) W[(p * M + b) * 32u] = e[b];
+  }
+  // zero test of the final value at tile position p
+  __device__ __forceinline__ void root_test(const uint32_t (&e)[M], uint32_t p) const
+  {
+    uint32_t nz = 0u;
+#pragma unroll
+    for (int b = 0; b < M; ++b) nz |= e[b];
+    uint32_t roots = ~nz & active;
+    if (!roots) return;
+    const uint32_t where = errloc[tile0 + p];
+    if (where == 0xFFFFFFFFu) return;
+    while (roots) {
+      const uint32_t bit = (uint32_t)__ffs((int)roots) - 1u;
+      roots &= roots - 1u;
+      const uint32_t cw = list[bit];
+      const uint32_t idx = atomicAdd(&count[cw], 1u);
+      if (idx < pos_stride) positions[(size_t)cw * pos_stride + idx] = where;
+    }
+  }
+  // BF(d), BF(d-1) on block bw (0..7) of the tile
+  __device__ __forceinline__ void radix4(uint32_t d, uint32_t bw, bool from_f, bool last) const
+  {
+    const uint32_t lb = d - 1u;
+    const uint32_t p0 = ((bw >> lb) << (lb + 2u)) | (bw & ((1u << lb) - 1u));
+    const uint32_t o = 1u << lb;
+    uint32_t e0[M], e1[M], e2[M], e3[M];
+    load(e0, p0, from_f);
+    load(e1, p0 + o, from_f);
+    load(e2, p0 + 2u * o, from_f);
+    load(e3, p0 + 3u * o, from_f);
+    const uint32_t gp = tile0 + p0;
+    const uint32_t G = gam[gam_off[d] + (gp >> (d + 1u))];
+    if (G) {
+      bs_mad_uniform<M>(e0, e2, G);
+      bs_mad_uniform<M>(e1, e3, G);
+    }
+#pragma unroll
+    for (int b = 0; b < M; ++b) {
+      e2[b] ^= e0[b];
+      e3[b] ^= e1[b];
+    }
+    const uint32_t Ga = gam[gam_off[d - 1u] + (gp >> d)], Gb = gam[gam_off[d - 1u] + (gp >> d) + 1u];
+    if (Ga) bs_mad_uniform<M>(e0, e1, Ga);
+    if (Gb) bs_mad_uniform<M>(e2, e3, Gb);
+#pragma unroll
+    for (int b = 0; b < M; ++b) {
+      e1[b] ^= e0[b];
+      e3[b] ^= e2[b];
+    }
+    if (last) {
+      root_test(e0, p0);
+      root_test(e1, p0 + o);
+      root_test(e2, p0 + 2u * o);
+      root_test(e3, p0 + 3u * o);
+    } else {
+      store(e0, p0);
+      store(e1, p0 + o);
+      store(e2, p0 + 2u * o);
+      store(e3, p0 + 3u * o);
+    }
+  }
+  // BF(0) on pair pw (0..15) of the tile; always the last step
+  __device__ __forceinline__ void radix2_last(uint32_t pw, bool from_f) const
+  {
+    const uint32_t p0 = pw << 1;
+    uint32_t lo[M], hi[M];
+    load(lo, p0, from_f);
+    load(hi, p0 + 1u, from_f);
+    const uint32_t G = gam[gam_off[0] + ((tile0 + p0) >> 1)];
+    if (G) bs_mad_uniform<M>(lo, hi, G);
+#pragma unroll
+    for (int b = 0; b < M; ++b) hi[b] ^= lo[b];
+    root_test(lo, p0);
+    root_test(hi, p0 + 1u);
+  }
+};
+
+// grid = (tile ranges per group, upper bound of the number of groups); dynamic smem =
+// 32 * M * 32 words.  ngroups_max >= sum_K ceil(ceil(count_K / 32) / 32).
+template <int M>
+__global__ void __launch_bounds__(BCHFFT_NT_LOC, BCHFFT_MINB_LOC)
+k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
+           const uint32_t *__restrict__ lists, uint32_t batch, uint32_t kmax, FftTables tab,
+           const uint32_t *__restrict__ errloc, uint32_t *__restrict__ count,
+           uint32_t *__restrict__ positions, uint32_t pos_stride)
+{
+  BCHFFT_DYN_SMEM(uint32_t, Wbuf);
+  // group -> (bucket K, group within the bucket)
+  uint32_t v = blockIdx.y, K = 1u;
+  for (; K <= kmax; ++K) {
+    const uint32_t ng = (((counts[K] + 31u) >> 5) + 31u) >> 5;
+    if (v < ng) break;
+    v -= ng;
+  }
+  if (K > kmax) return;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t pop = counts[K];
+  const uint32_t slab = v * 32u + lane;                 // slab of this lane within the bucket
+  const uint32_t first = slab * 32u;
+  LocU<M> job;
+  job.F2g = F2 + f2_index(blockIdx.y, kmax, 0u, M, 0u, lane);
+  job.W = Wbuf + lane;
+  job.gam = tab.gam;
+  job.gam_off = tab.gam_off;
+  job.errloc = errloc;
+  job.list = lists + (size_t)K * batch + first;
+  job.count = count;
+  job.positions = positions;
+  job.pos_stride = pos_stride;
+  job.kmask = (1u << K) - 1u;
+  job.active = first >= pop ? 0u : (pop - first >= 32u ? 0xFFFFFFFFu : ((1u << (pop - first)) - 1u));
+  const uint32_t ntiles = (1u << M) >> 5;
+  const uint32_t per = (ntiles + gridDim.x - 1u) / gridDim.x;
+  const uint32_t t_begin = blockIdx.x * per, t_end = (t_begin + per < ntiles) ? t_begin + per : ntiles;
+  for (uint32_t tile = t_begin; tile < t_end; ++tile) {
+    job.tile0 = tile << 5;
+    if (K == 5u) {
+      for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(4u, b, true, false);
+      __syncthreads();
+      for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(2u, b, false, false);
+      __syncthreads();
+      for (uint32_t b = warp; b < 16u; b += nwarps) job.radix2_last(b, false);
+      __syncthreads();
+    } else if (K == 4u) {
+      for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(3u, b, true, false);
+      __syncthreads();
+      for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(1u, b, false, true);
+      __syncthreads();
+    } else if (K == 3u) {
+      for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(2u, b, true, false);
+      __syncthreads();
+      for (uint32_t b = warp; b < 16u; b += nwarps) job.radix2_last(b, false);
+      __syncthreads();
+    } else if (K == 2u) {
+      for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(1u, b, true, true);
+    } else {
+      for (uint32_t b = warp; b < 16u; b += nwarps) job.radix2_last(b, true);
+    }
+  }
+}
+
 // ---- verdict + correction (bch.c:531-561) ---------------------------------------------------
 // ok = 1, corrected = 0 for a clean word; L > t -> ok = 0, corrected = 0; otherwise corrected =
 // #roots and the bits are flipped iff #roots == L.  Flips outside the packed array (only

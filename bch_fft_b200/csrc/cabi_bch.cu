@@ -156,9 +156,13 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
   }
   const unsigned ns = (unsigned)((cnt + 31) / 32);
   const unsigned nvirt = ns + (unsigned)kmax;           // sum_K ceil(count_K / 32) <= ns + kmax
+  // low locator degrees: lanes = slabs, warp-uniform multipliers (k_locate_u)
+  const char *uenv = getenv("BCHFFT_LOCATE_U");
+  const bool use_u = kmax <= kLocUMaxK && M >= 5 && !(uenv && atoi(uenv) == 0);
+  const unsigned ngroups = (unsigned)(cnt / 1024) + (unsigned)kmax + 1u;   // >= sum_K ceil(ceil(count_K/32)/32)
   // work buffer: butterfly descriptors, bucket counts, bucket lists, forward values
   const size_t desc_bytes = (sizeof(PassDesc) * (kMaxBuckets + 1) + 255) & ~(size_t)255;
-  const size_t f_words = ((size_t)nvirt << kmax) * PS;
+  const size_t f_words = use_u ? (((size_t)ngroups << kmax) * M * 32u) : (((size_t)nvirt << kmax) * PS);
   const size_t need = desc_bytes + ((kMaxBuckets + 1) + (size_t)(kMaxBuckets + 1) * cnt + f_words) * 4 + 256;
   int rc = w.fwd_buf.reserve(need);
   if (rc) return rc;
@@ -181,6 +185,28 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
   BCHFFT_CUDA_TRY(cudaMemsetAsync(counts, 0, (kMaxBuckets + 1) * 4, st));
   BCHFFT_RUN(k_bucket, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, (const int32_t *)s.flag,
              (const uint32_t *)s.L, tcap, (uint32_t)cnt, counts, lists);
+  if (use_u) {
+    for (int K = 1; K <= kmax; K++) {
+      uint32_t sb = 0;
+      while ((1u << (K + sb)) < 256u) sb++;
+      const size_t smem_f = sizeof(uint32_t) * M * ((size_t)1 << (K + sb));
+      BCHFFT_ENSURE_SMEM(k_elp_fwd_u<M>, c->f->device, smem_f);
+      BCHFFT_RUN(k_elp_fwd_u<M>, dim3((ns + (1u << sb) - 1u) >> sb), dim3(256), smem_f, st,
+                 (const uint32_t *)s.elp, (const uint32_t *)s.L, c->d, (const uint32_t *)counts,
+                 (const uint32_t *)lists, (uint32_t)cnt, sb, (uint32_t)kmax, c->f->tab, fwd[K], F);
+    }
+    // enough CTAs per group to fill the machine and to even out the buckets' different costs
+    const unsigned ntiles = (1u << M) >> 5;
+    unsigned gx = (2400u + ngroups - 1u) / ngroups;
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1u) gx = 1u;
+    const size_t smem_u = sizeof(uint32_t) * 32u * M * 32u;
+    BCHFFT_ENSURE_SMEM(k_locate_u<M>, c->f->device, smem_u);
+    BCHFFT_RUN(k_locate_u<M>, dim3(gx, ngroups), dim3(kNtLoc), smem_u, st, (const uint32_t *)F,
+               (const uint32_t *)counts, (const uint32_t *)lists, (uint32_t)cnt, (uint32_t)kmax, c->f->tab,
+               (const uint32_t *)c->f->d_errloc, s.count, s.positions, s.pos_stride);
+    return BCHFFT_OK;
+  }
   for (int K = 1; K <= kmax; K++) {
     // forward phase: 2^sb slabs per CTA so that a CTA has 256 coefficient columns to work on
     uint32_t sb = 0;
