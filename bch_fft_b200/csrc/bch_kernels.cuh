@@ -405,6 +405,11 @@ k_locate(const uint32_t *__restrict__ F, const uint32_t *__restrict__ counts,
 // [32 positions][M planes][32 lanes] shared-memory buffer (first step reads the forward values,
 // last step feeds the zero test).
 constexpr int kLocUMaxK = 5;
+#ifdef BCHFFT_EMU
+constexpr uint32_t kLocUQueue = 24;     // emulator build: tiny queue, so the tests take the drain and overflow paths
+#else
+constexpr uint32_t kLocUQueue = 6144;   // root queue entries per CTA
+#endif
 
 // F2 index of (group, coefficient i, plane b, lane)
 __device__ __forceinline__ size_t f2_index(uint32_t group, uint32_t kmax, uint32_t i, uint32_t M_, uint32_t b,
@@ -464,6 +469,26 @@ k_elp_fwd_u(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin, 
   }
 }
 
+// Drain the CTA's root queue: entry -> (codeword, reported position); every thread takes
+// independent entries, so the global atomics overlap.  Called by all threads after a barrier.
+__device__ __forceinline__ void locu_flush(const uint32_t *queue, uint32_t *qn, const uint32_t *__restrict__ glist,
+                                           const uint32_t *__restrict__ errloc, uint32_t *__restrict__ count,
+                                           uint32_t *__restrict__ positions, uint32_t pos_stride)
+{
+  const uint32_t n = *qn < kLocUQueue ? *qn : kLocUQueue;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t e = queue[i];
+    const uint32_t where = errloc[e >> 10];
+    if (where == 0xFFFFFFFFu) continue;   // the point 0: C(0) = 1, never a root of an active codeword
+    const uint32_t cw = glist[e & 1023u];
+    const uint32_t idx = atomicAdd(&count[cw], 1u);
+    if (idx < pos_stride) positions[(size_t)cw * pos_stride + idx] = where;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *qn = 0u;
+  __syncthreads();
+}
+
 template <int M>
 struct LocU {
   // per-thread view of the job
@@ -471,10 +496,10 @@ struct LocU {
   uint32_t *W;                // shared buffer (+ lane)
   const uint32_t *gam;
   const uint32_t *gam_off;
-  const uint32_t *errloc;
-  const uint32_t *list;       // codeword indices of this lane's slab
+  uint32_t *queue, *qn;       // shared root queue of the CTA: (tile position << 10) | codeword of the group
+  const uint32_t *glist, *errloc;   // overflow path: the group's codeword list, position table
   uint32_t *count, *positions;
-  uint32_t active, pos_stride, kmask, tile0;
+  uint32_t active, kmask, tile0, lane, pos_stride;
 
   __device__ __forceinline__ void load(uint32_t (&e)[M], uint32_t p, bool from_f) const
   {
@@ -492,22 +517,29 @@ struct LocU {
 #pragma unroll
     for (int b = 0; b < M; ++b) W[(p * M + b) * 32u] = e[b];
   }
-  // zero test of the final value at tile position p
+  // zero test of the final value at tile position p.  Roots go to the CTA's shared queue (one
+  // shared-memory atomic each); the global bookkeeping happens once per CTA in locu_flush.
   __device__ __forceinline__ void root_test(const uint32_t (&e)[M], uint32_t p) const
   {
     uint32_t nz = 0u;
 #pragma unroll
     for (int b = 0; b < M; ++b) nz |= e[b];
     uint32_t roots = ~nz & active;
-    if (!roots) return;
-    const uint32_t where = errloc[tile0 + p];
-    if (where == 0xFFFFFFFFu) return;
     while (roots) {
       const uint32_t bit = (uint32_t)__ffs((int)roots) - 1u;
       roots &= roots - 1u;
-      const uint32_t cw = list[bit];
-      const uint32_t idx = atomicAdd(&count[cw], 1u);
-      if (idx < pos_stride) positions[(size_t)cw * pos_stride + idx] = where;
+      const uint32_t slot = atomicAdd(qn, 1u);
+      if (slot < kLocUQueue) {
+        queue[slot] = ((tile0 + p) << 10) | (lane << 5) | bit;
+      } else {
+        // queue full (only with pathological root clustering): record directly
+        const uint32_t where = errloc[tile0 + p];
+        if (where != 0xFFFFFFFFu) {
+          const uint32_t cw = glist[(lane << 5) | bit];
+          const uint32_t idx = atomicAdd(&count[cw], 1u);
+          if (idx < pos_stride) positions[(size_t)cw * pos_stride + idx] = where;
+        }
+      }
     }
   }
   // BF(d), BF(d-1) on block bw (0..7) of the tile
@@ -578,6 +610,10 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
            uint32_t *__restrict__ positions, uint32_t pos_stride)
 {
   BCHFFT_DYN_SMEM(uint32_t, Wbuf);
+  uint32_t *queue = Wbuf + 32u * M * 32u;
+  __shared__ uint32_t s_qn;
+  if (threadIdx.x == 0) s_qn = 0u;
+  __syncthreads();
   // group -> (bucket K, group within the bucket)
   uint32_t v = blockIdx.y, K = 1u;
   for (; K <= kmax; ++K) {
@@ -595,18 +631,30 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
   job.W = Wbuf + lane;
   job.gam = tab.gam;
   job.gam_off = tab.gam_off;
+  job.queue = queue;
+  job.qn = &s_qn;
+  job.lane = lane;
+  job.kmask = (1u << K) - 1u;
+  const uint32_t *glist = lists + (size_t)K * batch + (size_t)v * 1024u;   // the group's codewords
+  job.glist = glist;
   job.errloc = errloc;
-  job.list = lists + (size_t)K * batch + first;
   job.count = count;
   job.positions = positions;
   job.pos_stride = pos_stride;
-  job.kmask = (1u << K) - 1u;
   job.active = first >= pop ? 0u : (pop - first >= 32u ? 0xFFFFFFFFu : ((1u << (pop - first)) - 1u));
   const uint32_t ntiles = (1u << M) >> 5;
   const uint32_t per = (ntiles + gridDim.x - 1u) / gridDim.x;
   const uint32_t t_begin = blockIdx.x * per, t_end = (t_begin + per < ntiles) ? t_begin + per : ntiles;
   for (uint32_t tile = t_begin; tile < t_end; ++tile) {
     job.tile0 = tile << 5;
+    // every eighth tile: drain the queue when it is half full (uniform decision behind a barrier;
+    // about 32 roots per tile are expected, an overflow in between takes the direct path)
+    if ((tile & 7u) == 7u) {
+      __syncthreads();
+      const uint32_t fill = s_qn;
+      __syncthreads();   // nobody pushes before everybody has read the fill level
+      if (fill > kLocUQueue / 2u) locu_flush(queue, &s_qn, glist, errloc, count, positions, pos_stride);
+    }
     if (K == 5u) {
       for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(4u, b, true, false);
       __syncthreads();
@@ -630,6 +678,8 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
       for (uint32_t b = warp; b < 16u; b += nwarps) job.radix2_last(b, true);
     }
   }
+  __syncthreads();
+  locu_flush(queue, &s_qn, glist, errloc, count, positions, pos_stride);
 }
 
 // ---- verdict + correction (bch.c:531-561) ---------------------------------------------------

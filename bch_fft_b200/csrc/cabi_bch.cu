@@ -158,7 +158,7 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
   const unsigned nvirt = ns + (unsigned)kmax;           // sum_K ceil(count_K / 32) <= ns + kmax
   // low locator degrees: lanes = slabs, warp-uniform multipliers (k_locate_u)
   const char *uenv = getenv("BCHFFT_LOCATE_U");
-  const bool use_u = kmax <= kLocUMaxK && M >= 5 && !(uenv && atoi(uenv) == 0);
+  const bool use_u = kmax <= kLocUMaxK && M >= 5 && M <= 22 && !(uenv && atoi(uenv) == 0);
   const unsigned ngroups = (unsigned)(cnt / 1024) + (unsigned)kmax + 1u;   // >= sum_K ceil(ceil(count_K/32)/32)
   // work buffer: butterfly descriptors, bucket counts, bucket lists, forward values
   const size_t desc_bytes = (sizeof(PassDesc) * (kMaxBuckets + 1) + 255) & ~(size_t)255;
@@ -200,7 +200,7 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
     unsigned gx = (2400u + ngroups - 1u) / ngroups;
     if (gx > ntiles) gx = ntiles;
     if (gx < 1u) gx = 1u;
-    const size_t smem_u = sizeof(uint32_t) * 32u * M * 32u;
+    const size_t smem_u = sizeof(uint32_t) * (32u * M * 32u + kLocUQueue);
     BCHFFT_ENSURE_SMEM(k_locate_u<M>, c->f->device, smem_u);
     BCHFFT_RUN(k_locate_u<M>, dim3(gx, ngroups), dim3(kNtLoc), smem_u, st, (const uint32_t *)F,
                (const uint32_t *)counts, (const uint32_t *)lists, (uint32_t)cnt, (uint32_t)kmax, c->f->tab,
