@@ -408,7 +408,7 @@ constexpr int kLocUMaxK = 5;
 #ifdef BCHFFT_EMU
 constexpr uint32_t kLocUQueue = 24;     // emulator build: tiny queue, so the tests take the drain and overflow paths
 #else
-constexpr uint32_t kLocUQueue = 6144;   // root queue entries per CTA
+constexpr uint32_t kLocUQueue = 4096;   // root queue entries per CTA
 #endif
 
 // F2 index of (group, coefficient i, plane b, lane)
@@ -555,10 +555,7 @@ struct LocU {
     load(e3, p0 + 3u * o, from_f);
     const uint32_t gp = tile0 + p0;
     const uint32_t G = gam[gam_off[d] + (gp >> (d + 1u))];
-    if (G) {
-      bs_mad_uniform<M>(e0, e2, G);
-      bs_mad_uniform<M>(e1, e3, G);
-    }
+    if (G) bs_mad_uniform2<M>(e0, e2, e1, e3, G);
 #pragma unroll
     for (int b = 0; b < M; ++b) {
       e2[b] ^= e0[b];
@@ -603,7 +600,7 @@ struct LocU {
 // grid = (tile ranges per group, upper bound of the number of groups); dynamic smem =
 // 32 * M * 32 words.  ngroups_max >= sum_K ceil(ceil(count_K / 32) / 32).
 template <int M>
-__global__ void __launch_bounds__(BCHFFT_NT_LOC, BCHFFT_MINB_LOC)
+__global__ void __launch_bounds__(BCHFFT_NT_LOC, BCHFFT_MINB_LOCU)
 k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
            const uint32_t *__restrict__ lists, uint32_t batch, uint32_t kmax, FftTables tab,
            const uint32_t *__restrict__ errloc, uint32_t *__restrict__ count,
@@ -642,6 +639,7 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
   job.positions = positions;
   job.pos_stride = pos_stride;
   job.active = first >= pop ? 0u : (pop - first >= 32u ? 0xFFFFFFFFu : ((1u << (pop - first)) - 1u));
+  const uint32_t nsteps = (K + 1u) >> 1;
   const uint32_t ntiles = (1u << M) >> 5;
   const uint32_t per = (ntiles + gridDim.x - 1u) / gridDim.x;
   const uint32_t t_begin = blockIdx.x * per, t_end = (t_begin + per < ntiles) ? t_begin + per : ntiles;
@@ -655,27 +653,23 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
       __syncthreads();   // nobody pushes before everybody has read the fill level
       if (fill > kLocUQueue / 2u) locu_flush(queue, &s_qn, glist, errloc, count, positions, pos_stride);
     }
-    if (K == 5u) {
-      for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(4u, b, true, false);
-      __syncthreads();
-      for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(2u, b, false, false);
-      __syncthreads();
-      for (uint32_t b = warp; b < 16u; b += nwarps) job.radix2_last(b, false);
-      __syncthreads();
-    } else if (K == 4u) {
-      for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(3u, b, true, false);
-      __syncthreads();
-      for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(1u, b, false, true);
-      __syncthreads();
-    } else if (K == 3u) {
-      for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(2u, b, true, false);
-      __syncthreads();
-      for (uint32_t b = warp; b < 16u; b += nwarps) job.radix2_last(b, false);
-      __syncthreads();
-    } else if (K == 2u) {
-      for (uint32_t b = warp; b < 8u; b += nwarps) job.radix4(1u, b, true, true);
-    } else {
-      for (uint32_t b = warp; b < 16u; b += nwarps) job.radix2_last(b, true);
+    // steps: level pairs (d, d-1) as radix-4 blocks, a trailing level 0 as radix-2 pairs.  One
+    // rolled loop, so that the kernel holds a single copy of each multiply body (the code of all
+    // buckets then shares the instruction cache).
+#pragma unroll 1
+    for (uint32_t s = 0; s < nsteps; ++s) {
+      const uint32_t d = K - 1u - 2u * s;
+      const bool from_f = s == 0u, last = s + 1u == nsteps;
+      if (d >= 1u) {
+#pragma unroll 1
+        for (uint32_t b = 0; b < 8u; ++b)
+          if ((b & (nwarps - 1u)) == warp) job.radix4(d, b, from_f, last);
+      } else {
+#pragma unroll 1
+        for (uint32_t b = 0; b < 16u; ++b)
+          if ((b & (nwarps - 1u)) == warp) job.radix2_last(b, from_f);
+      }
+      if (nsteps > 1u) __syncthreads();   // also keeps the next tile's first step off a buffer still being read
     }
   }
   __syncthreads();

@@ -51,6 +51,9 @@
 #ifndef BCHFFT_MINB_LOC
 #define BCHFFT_MINB_LOC 2
 #endif
+#ifndef BCHFFT_MINB_LOCU
+#define BCHFFT_MINB_LOCU 3
+#endif
 #ifndef BCHFFT_NT_SYN
 #define BCHFFT_NT_SYN 256
 #endif
@@ -212,6 +215,66 @@ __device__ __forceinline__ void bs_mad_uniform(uint32_t (&acc)[M], const uint32_
   bs_reduce<M>(q);
 #pragma unroll
   for (int i = 0; i < M; ++i) acc[i] = q[i];
+}
+
+// two multiply-adds with the same warp-uniform constant (the two butterflies of a radix-4 block
+// that share a multiplier): one branch sequence, twice the independent work per branch
+template <int M>
+__device__ __forceinline__ void bs_mad_uniform2(uint32_t (&acc0)[M], const uint32_t (&a0)[M],
+                                                uint32_t (&acc1)[M], const uint32_t (&a1)[M], uint32_t c)
+{
+  uint32_t p[2 * M], r[2 * M];
+#pragma unroll
+  for (int k = 0; k < 2 * M; ++k) {
+    p[k] = (k < M) ? acc0[k] : 0u;
+    r[k] = (k < M) ? acc1[k] : 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < M; j += 2) {
+    const uint32_t two = (c >> j) & 3u;
+    if (j + 1 == M) {
+      if (two & 1u) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+          p[i + j] ^= a0[i];
+          r[i + j] ^= a1[i];
+        }
+      }
+    } else if (two == 1u) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        p[i + j] ^= a0[i];
+        r[i + j] ^= a1[i];
+      }
+    } else if (two == 2u) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        p[i + j + 1] ^= a0[i];
+        r[i + j + 1] ^= a1[i];
+      }
+    } else if (two == 3u) {
+      p[j] ^= a0[0];
+      r[j] ^= a1[0];
+#pragma unroll
+      for (int i = 1; i < M; ++i) {
+        p[i + j] = xor3(p[i + j], a0[i], a0[i - 1]);
+        r[i + j] = xor3(r[i + j], a1[i], a1[i - 1]);
+      }
+      p[j + M] ^= a0[M - 1];
+      r[j + M] ^= a1[M - 1];
+    }
+  }
+  uint32_t q[2 * M - 1];
+#pragma unroll
+  for (int k = 0; k < 2 * M - 1; ++k) q[k] = p[k];
+  bs_reduce<M>(q);
+#pragma unroll
+  for (int i = 0; i < M; ++i) acc0[i] = q[i];
+#pragma unroll
+  for (int k = 0; k < 2 * M - 1; ++k) q[k] = r[k];
+  bs_reduce<M>(q);
+#pragma unroll
+  for (int i = 0; i < M; ++i) acc1[i] = q[i];
 }
 
 // In-place transpose of a 32x32 bit matrix held as 32 words, LSB-first: afterwards bit j of
