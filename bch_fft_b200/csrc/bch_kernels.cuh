@@ -116,6 +116,121 @@ k_syndrome(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32
   if (threadIdx.x == 0 && s_par) atomicXor(&parity[slab], s_par);
 }
 
+
+// ---- syndromes through the universal LFSR (orders coprime to every j) -------------------------
+// When gcd(j, 2^M - 1) = 1 the map p -> e = j p mod (2^M - 1) permutes the positions, and
+//   S_j = sum_p c_p x^(j p) = ( sum_e c_(p(e)) X^e  mod  f(X) )(x),      p(e) = e j^-1 mod (2^M - 1),
+// f the field polynomial.  So every class runs the SAME LFSR -- division by f, whose taps are
+// compile-time constants (4 LOP3 per position for a pentanomial instead of M masked ones) -- on
+// the codeword read in permuted order, and the remainder IS the syndrome in the field's
+// polynomial basis.  The whole codeword of a slab sits in shared memory as plane words
+// (padded: word p + p/32); work item = (class, chunk of lc = ceil(order/32) consecutive e), the 32
+// lanes of a warp are the 32 chunks of one class; a chunk's remainder is shifted by x^(q lc) with
+// the fold constants (shared by all classes).  grid = slabs; dynamic smem =
+// (ceil(order / 32) * 33 + nodd * M) words.
+template <int M>
+__device__ __forceinline__ void lfsr_field_step(uint32_t (&s)[M], uint32_t in)
+{
+  constexpr uint32_t taps = field_poly(M) & ((1u << M) - 1u);
+  const uint32_t fb = s[M - 1];
+#pragma unroll
+  for (int b = M - 1; b >= 1; --b) s[b] = ((taps >> b) & 1u) ? (s[b - 1] ^ fb) : s[b - 1];
+  s[0] = in ^ fb;   // bit 0 of the field polynomial is always set
+}
+
+template <int M>
+__global__ void __launch_bounds__(BCHFFT_NT_SYN, BCHFFT_MINB_SYNP)
+k_syndrome_p(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32_t length_bits,
+             uint32_t batch, uint32_t nodd, uint32_t lc, const uint32_t *__restrict__ jinv,
+             const uint32_t *__restrict__ start_idx, const uint32_t *__restrict__ foldp,
+             const uint32_t *__restrict__ vbits, uint32_t *__restrict__ acc, uint32_t *__restrict__ parity)
+{
+  BCHFFT_DYN_SMEM(uint32_t, smem);
+  constexpr uint32_t order = (1u << M) - 1u;
+  const uint32_t slab = blockIdx.x;
+  const uint32_t ngrp = (order + 31u) / 32u;          // 32-position groups of the codeword
+  uint32_t *planes = smem;
+  uint32_t *sacc = smem + ngrp * 33u;                  // [nodd][M]
+  __shared__ uint32_t s_par;
+  if (threadIdx.x == 0) s_par = 0u;
+  for (uint32_t i = threadIdx.x; i < nodd * M; i += blockDim.x) sacc[i] = 0u;
+  __syncthreads();
+
+  // phase A: transpose 32 codewords x 32 positions blocks into plane words
+  uint32_t par = 0u;
+  for (uint32_t g = threadIdx.x; g < ngrp; g += blockDim.x) {
+    uint32_t x[32];
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const uint32_t item = slab * 32u + l;
+      x[l] = (item < batch && g < words32_per_cw) ? words32[(size_t)item * words32_per_cw + g] : 0u;
+    }
+    const uint32_t first = g * 32u;
+    if (first + 32u > length_bits) {
+      const uint32_t keep = first < length_bits ? length_bits - first : 0u;
+      const uint32_t mask = keep ? (0xFFFFFFFFu >> (32u - keep)) : 0u;
+#pragma unroll
+      for (int l = 0; l < 32; ++l) x[l] &= mask;
+    }
+    transpose32(x);
+    const uint32_t vw = (g < words32_per_cw) ? vbits[g] : 0u;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      planes[g * 33u + b] = x[b];
+      par ^= x[b] & (0u - ((vw >> b) & 1u));
+    }
+  }
+  if (par) atomicXor(&s_par, par);
+  __syncthreads();
+
+  // phase B
+  const uint32_t main_steps = lc > 32u ? ((lc - 32u) & ~7u) : 0u;
+  for (uint32_t item = threadIdx.x; item < nodd * 32u; item += blockDim.x) {
+    const uint32_t ji = item >> 5, q = item & 31u;
+    const uint32_t e0 = q * lc, e1 = (e0 + lc < order) ? e0 + lc : order;   // chunk [e0, e1)
+    const uint32_t nsteps = e1 > e0 ? e1 - e0 : 0u;
+    const uint32_t step = jinv[ji];
+    uint32_t idx = start_idx[item];        // p(e1 - 1)
+    uint32_t s[M];
+#pragma unroll
+    for (int b = 0; b < M; ++b) s[b] = 0u;
+    // descending e: s <- s X + c_(p(e));  p(e - 1) = p(e) - j^-1 mod order
+    const uint32_t pro = nsteps > main_steps ? nsteps - main_steps : 0u;
+    for (uint32_t k = 0; k < pro; ++k) {
+      lfsr_field_step<M>(s, planes[idx + (idx >> 5)]);
+      const uint32_t t = idx - step, t2 = t + order;
+      idx = t < t2 ? t : t2;   // unsigned min: t wrapped around 2^32 exactly when idx < step
+    }
+    if (nsteps >= main_steps) {
+      for (uint32_t k = 0; k < main_steps; k += 8u) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          lfsr_field_step<M>(s, planes[idx + (idx >> 5)]);
+          const uint32_t t = idx - step, t2 = t + order;
+          idx = t < t2 ? t : t2;
+        }
+      }
+    }
+    // shift by x^(q lc): out = sum_b s[b] * x^(q lc + b)
+    const uint32_t *fc = foldp + q * M;
+    uint32_t out[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) out[k] = 0u;
+#pragma unroll
+    for (int b = 0; b < M; ++b) {
+      const uint32_t c = fc[b];
+#pragma unroll
+      for (int k = 0; k < M; ++k) out[k] ^= s[b] & (0u - ((c >> k) & 1u));
+    }
+#pragma unroll
+    for (int k = 0; k < M; ++k)
+      if (out[k]) atomicXor(&sacc[ji * M + k], out[k]);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < nodd * M; i += blockDim.x) acc[(size_t)slab * nodd * M + i] = sacc[i];
+  if (threadIdx.x == 0) parity[slab] = s_par;
+}
+
 // One thread per codeword: syndromes[cw][0..d-1] (u32), flag[cw] (bch.c:317-324).
 // syndrome[0] (not a BCH syndrome; method dependent in the reference, see k_syndrome) comes from
 // the parity word.

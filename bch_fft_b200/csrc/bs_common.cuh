@@ -51,6 +51,9 @@
 #ifndef BCHFFT_MINB_LOC
 #define BCHFFT_MINB_LOC 2
 #endif
+#ifndef BCHFFT_MINB_SYNP
+#define BCHFFT_MINB_SYNP 3
+#endif
 #ifndef BCHFFT_MINB_LOCU
 #define BCHFFT_MINB_LOCU 3
 #endif

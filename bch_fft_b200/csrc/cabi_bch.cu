@@ -13,6 +13,11 @@ struct bchfft_code {
   uint32_t syn_fft_rule = 0; // reference would take its FFT syndrome path (bch.c:240-254)
   uint32_t chunk_pos = 0, nchunks = 0, nsub_total = 0;
   uint32_t *d_taps = nullptr, *d_fold = nullptr, *d_vbits = nullptr;
+  // universal-LFSR syndrome kernel (k_syndrome_p): usable when every odd j < d is coprime to the
+  // field order; per class j^-1 mod order, per (class, chunk) the first permuted position, per
+  // chunk the shift constants x^(q lc + b)
+  uint32_t syn_p = 0, syn_lc = 0;
+  uint32_t *d_jinv = nullptr, *d_start = nullptr, *d_foldp = nullptr;
   // work sets: [0] serves the device-pointer and stage-level entry points, [1] .. [3] are the
   // lanes of the pipelined host entry point (copy-in / decode / copy-out overlap)
   struct WorkSet {
@@ -115,6 +120,18 @@ static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, 
                            cudaStream_t st)
 {
   const unsigned ns = (unsigned)((cnt + 31) / 32);
+  const char *penv = getenv("BCHFFT_SYN_P");
+  if (c->syn_p && !(penv && atoi(penv) == 0)) {
+    const size_t smem_p = sizeof(uint32_t) * ((size_t)((c->f->order + 31u) / 32u) * 33u + (size_t)c->nodd * M);
+    BCHFFT_ENSURE_SMEM(k_syndrome_p<M>, c->f->device, smem_p);
+    BCHFFT_RUN(k_syndrome_p<M>, dim3(ns), dim3(kNtSyn), smem_p, st, (const uint32_t *)d_words, c->wpc * 2u,
+               c->length, (uint32_t)cnt, c->nodd, c->syn_lc, (const uint32_t *)c->d_jinv,
+               (const uint32_t *)c->d_start, (const uint32_t *)c->d_foldp, (const uint32_t *)c->d_vbits,
+               s.acc, s.parity);
+    BCHFFT_RUN(k_syn_finish<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
+               (const uint32_t *)s.acc, (const uint32_t *)s.parity, c->nodd, c->d, (uint32_t)cnt, s.syn, s.flag);
+    return BCHFFT_OK;
+  }
   const size_t smem = sizeof(uint32_t) * ((size_t)c->chunk_pos + c->chunk_pos / 32 + (size_t)c->nodd * M);
   BCHFFT_ENSURE_SMEM(k_syndrome<M>, c->f->device, smem);
   BCHFFT_RUN(k_syndrome<M>, dim3(c->nchunks, ns), dim3(kNtSyn), smem, st,
@@ -385,6 +402,45 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
   }
   cudaMemcpy(c->d_taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(c->d_fold, fold.data(), fold.size() * 4, cudaMemcpyHostToDevice);
+  // universal-LFSR syndromes: every class j must permute the positions (gcd(j, order) = 1), the
+  // whole codeword must fit shared memory, and no codeword bit may sit at position >= order
+  {
+    auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t r = a % b; a = b; b = r; } return a; };
+    bool ok = M >= 9 && M <= 15 && length <= order;
+    for (uint32_t ji = 0; ji < c->nodd && ok; ji++) ok = gcd((2u * ji + 1u) % order, order) == 1u;
+    const size_t smem_p = sizeof(uint32_t) * ((size_t)((order + 31u) / 32u) * 33u + (size_t)c->nodd * M);
+    if (ok && smem_p <= (size_t)200 * 1024) {
+      const uint32_t lc = (order + 31u) / 32u;
+      std::vector<uint32_t> jinv(c->nodd), start((size_t)c->nodd * 32u), foldp((size_t)32 * M);
+      for (uint32_t ji = 0; ji < c->nodd; ji++) {
+        const uint32_t j = (2u * ji + 1u) % order;
+        // j^-1 mod order by the extended Euclid
+        int64_t a = j, b = order, x0 = 1, x1 = 0;
+        while (b) { const int64_t qq = a / b, r = a % b; a = b; b = r; const int64_t x2 = x0 - qq * x1; x0 = x1; x1 = x2; }
+        const uint32_t inv = (uint32_t)(((x0 % (int64_t)order) + order) % order);
+        jinv[ji] = inv;
+        for (uint32_t q = 0; q < 32u; q++) {
+          const uint64_t e0 = (uint64_t)q * lc, e1 = e0 + lc < order ? e0 + lc : order;
+          start[(size_t)ji * 32u + q] = e1 > e0 ? (uint32_t)(((e1 - 1u) * (uint64_t)inv) % order) : 0u;
+        }
+      }
+      for (uint32_t q = 0; q < 32u; q++)
+        for (uint32_t b = 0; b < M; b++) foldp[(size_t)q * M + b] = f->h_exp[((uint64_t)q * lc + b) % order];
+      cudaError_t p0 = cudaMalloc((void **)&c->d_jinv, jinv.size() * 4 + 16);
+      cudaError_t p1 = cudaMalloc((void **)&c->d_start, start.size() * 4 + 16);
+      cudaError_t p2 = cudaMalloc((void **)&c->d_foldp, foldp.size() * 4 + 16);
+      if (p0 != cudaSuccess || p1 != cudaSuccess || p2 != cudaSuccess) {
+        set_error("bchfft_code_create: cudaMalloc failed");
+        bchfft_code_destroy(c);
+        return BCHFFT_ERR_CUDA;
+      }
+      cudaMemcpy(c->d_jinv, jinv.data(), jinv.size() * 4, cudaMemcpyHostToDevice);
+      cudaMemcpy(c->d_start, start.data(), start.size() * 4, cudaMemcpyHostToDevice);
+      cudaMemcpy(c->d_foldp, foldp.data(), foldp.size() * 4, cudaMemcpyHostToDevice);
+      c->syn_lc = lc;
+      c->syn_p = 1u;
+    }
+  }
   *out = c;
   return BCHFFT_OK;
 }
@@ -397,6 +453,9 @@ extern "C" void bchfft_code_destroy(bchfft_code *c)
   cudaFree(c->d_taps);
   cudaFree(c->d_fold);
   cudaFree(c->d_vbits);
+  cudaFree(c->d_jinv);
+  cudaFree(c->d_start);
+  cudaFree(c->d_foldp);
   for (auto &w : c->work) {
     w.scratch.release();
     w.fwd_buf.release();
