@@ -8,6 +8,7 @@
 //                  additive FFT, root compaction (bch.c:406-490)
 //   k_correct      ok / corrected bookkeeping and the bit flips (bch.c:531-561)
 #pragma once
+#include <type_traits>
 #include "bs_common.cuh"
 #include "fft_kernels.cuh"
 
@@ -269,40 +270,87 @@ __global__ void k_syn_finish(const uint32_t *__restrict__ acc, const uint32_t *_
 // reproduced from zero-initialised buffers).  bm: [3][d+1][batch] scratch, zero on entry
 // (coefficient-major: threads of a warp touch consecutive words).  Outputs: L[cw] and
 // elp[cw][0..d] = the final C buffer.
-template <int M>
+// Both operands of the multiplies are data here, so this is the one place that uses the
+// reference's log/exp formulation (finite_field.c:59-70).
+//   SM = true  (fields up to GF(2^14), d small enough): everything a thread touches lives in
+//        shared memory -- 16-bit log / exp tables staged by the CTA, the three coefficient buffers
+//        and the syndromes as [index][thread] columns (conflict-free) -- so the recurrence runs at
+//        shared-memory latency.  dynamic smem = 2 * (2^(M+1) + (4 d + 3) * threads) bytes.
+//   SM = false: coefficient buffers in the zero-initialised global scratch bm: [3][d+1][batch]
+//        (coefficient-major), table-free shift-and-add multiply.
+template <int M, bool SM>
 __global__ void k_bm(const uint32_t *__restrict__ syn, const int32_t *__restrict__ flag, uint32_t d,
                      uint32_t batch, const uint32_t *__restrict__ gexp, const uint32_t *__restrict__ glog,
                      uint32_t *__restrict__ bm, uint32_t *__restrict__ elp, uint32_t *__restrict__ Lout)
 {
-  const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cw >= batch) return;
+  typedef typename std::conditional<SM, uint16_t, uint32_t>::type coef_t;
   const uint32_t order = (1u << M) - 1u;
-  const size_t cs = batch;                 // stride between coefficients
-  const size_t bs = (size_t)(d + 1) * cs;  // stride between buffers
-  uint32_t *A = bm + cw, *B = A + bs, *C = B + bs;
-  const uint32_t *s = syn + (size_t)cw * d;
+  BCHFFT_DYN_SMEM(uint16_t, tabs);
+  uint16_t *slog = tabs, *sexp = tabs + (1u << M);
+  const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t cs = SM ? (size_t)blockDim.x : (size_t)batch;   // stride between coefficients
+  const size_t bs = (size_t)(d + 1) * cs;                       // stride between buffers
+  coef_t *A, *B, *C;
+  const coef_t *s;
+  if (SM) {
+    for (uint32_t i = threadIdx.x; i <= order; i += blockDim.x) {
+      slog[i] = (uint16_t)glog[i];
+      sexp[i] = (uint16_t)gexp[i];
+    }
+    coef_t *poly = (coef_t *)(tabs + (2u << M)) + threadIdx.x;
+    A = poly;
+    B = A + bs;
+    C = B + bs;
+    coef_t *sc = C + bs;
+    for (uint32_t j = 0; j < 3u * (d + 1u); ++j) poly[j * cs] = 0;
+    for (uint32_t j = 0; j < d; ++j) sc[j * cs] = (coef_t)(cw < batch ? syn[(size_t)cw * d + j] : 0u);
+    s = sc;
+    __syncthreads();
+  } else {
+    A = (coef_t *)bm + cw;
+    B = A + bs;
+    C = B + bs;
+    s = (const coef_t *)syn + (size_t)cw * d;
+  }
+  const size_t ss = SM ? cs : 1;   // stride between syndromes
+  auto mul = [&](uint32_t a, uint32_t b) -> uint32_t {
+    if (!SM) return gf_mul<M>(a, b);
+    if (!a || !b) return 0u;
+    uint32_t lg = (uint32_t)slog[a] + (uint32_t)slog[b];
+    if (lg >= order) lg -= order;
+    return sexp[lg];
+  };
+  // a * x^lg (= a * elem)
+  auto mul_log = [&](uint32_t a, uint32_t lg, uint32_t elem) -> uint32_t {
+    if (!SM) return gf_mul<M>(a, elem);
+    if (!a) return 0u;
+    lg += slog[a];
+    if (lg >= order) lg -= order;
+    return sexp[lg];
+  };
+  if (cw >= batch) return;
   uint32_t L = 0;
   if (flag[cw]) {
     uint32_t degA = 0, degB = 0, degC = 0, gap = 1, inv_b_log = 0;
     B[0] = 1u;
     C[0] = 1u;
     for (uint32_t i = 0; i + 1 < d; ++i) {
-      uint32_t disc = s[i + 1];
-      for (uint32_t j = 1; j <= degC; ++j) disc ^= gf_mul<M>(C[j * cs], s[i + 1 - j]);
+      uint32_t disc = s[(i + 1) * ss];
+      for (uint32_t j = 1; j <= degC; ++j) disc ^= mul(C[j * cs], s[(i + 1 - j) * ss]);
       if (!disc) {
         gap++;
         continue;
       }
-      const uint32_t dlog = glog[disc];
+      const uint32_t dlog = SM ? (uint32_t)slog[disc] : glog[disc];
       uint32_t sl = dlog + inv_b_log;
       if (sl >= order) sl -= order;
-      const uint32_t scale = gexp[sl];
+      const uint32_t scale = SM ? (uint32_t)sexp[sl] : gexp[sl];
       const uint32_t hiB = degB + gap;
       const uint32_t keep = gap < degC + 1 ? gap : degC + 1;
       uint32_t j = 0;
       for (; j < keep; ++j) A[j * cs] = C[j * cs];
       for (; j < gap; ++j) A[j * cs] = 0u;
-      for (; j <= hiB; ++j) A[j * cs] = gf_mul<M>(B[(j - gap) * cs], scale);
+      for (; j <= hiB; ++j) A[j * cs] = (coef_t)mul_log(B[(j - gap) * cs], sl, scale);
       for (; j <= degC; ++j) A[j * cs] = 0u;
       if (degC != hiB) {
         degA = degC > hiB ? degC : hiB;
@@ -310,20 +358,20 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, const int32_t *__restrict
       } else {
         for (j = gap; j <= degC; ++j) {
           const uint32_t v = A[j * cs] ^ C[j * cs];
-          A[j * cs] = v;
+          A[j * cs] = (coef_t)v;
           if (v) degA = j;
         }
       }
       if (2u * L <= i) {
         L = i + 1u - L;
         degB = degC;
-        uint32_t *t = B; B = C; C = t;
+        coef_t *t = B; B = C; C = t;
         inv_b_log = order - dlog;
         gap = 1;
       } else {
         gap++;
       }
-      { uint32_t *t = C; C = A; A = t; }
+      { coef_t *t = C; C = A; A = t; }
       degC = degA;
     }
   } else {

@@ -1,5 +1,6 @@
 // Batched BCH decode driver (see include/bchfft_cuda.h, bchfft_code_* / bchfft_bch_*).
 #include <stdlib.h>
+#include <type_traits>
 #include <string.h>
 
 #include "cabi_common.h"
@@ -147,9 +148,25 @@ static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, 
 template <int M>
 static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t st)
 {
-  BCHFFT_RUN(k_bm<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
-                (const uint32_t *)s.syn, (const int32_t *)s.flag, c->d, (uint32_t)cnt,
-                (const uint32_t *)c->f->d_exp, (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L);
+  // shared-memory variant when the tables and the per-thread columns fit next to each other twice per SM
+#ifdef BCHFFT_EMU
+  const unsigned nt = 32;
+#else
+  const unsigned nt = 256;
+#endif
+  const size_t smem = sizeof(uint16_t) * (((size_t)2 << M) + (size_t)(4 * c->d + 3) * nt);
+  const char *benv = getenv("BCHFFT_BM_SM");
+  if (M <= 14 && smem <= (size_t)110 * 1024 && !(benv && atoi(benv) == 0)) {
+    constexpr bool kSm = M <= 14;
+    BCHFFT_ENSURE_SMEM((k_bm<M, kSm>), c->f->device, smem);
+    BCHFFT_RUN((k_bm<M, kSm>), dim3((unsigned)((cnt + nt - 1) / nt)), dim3(nt), smem, st,
+               (const uint32_t *)s.syn, (const int32_t *)s.flag, c->d, (uint32_t)cnt,
+               (const uint32_t *)c->f->d_exp, (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L);
+  } else {
+    BCHFFT_RUN((k_bm<M, false>), dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
+               (const uint32_t *)s.syn, (const int32_t *)s.flag, c->d, (uint32_t)cnt,
+               (const uint32_t *)c->f->d_exp, (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L);
+  }
   return BCHFFT_OK;
 }
 

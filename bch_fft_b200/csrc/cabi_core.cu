@@ -137,6 +137,7 @@ extern "C" int bchfft_profile_end(void)
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
     std::string nm(r.name);
+    if (!nm.empty() && nm[0] == '(') nm = nm.substr(1);   // "(kernel<A, B>)": template-id with a comma
     const size_t lt = nm.find('<');
     if (lt != std::string::npos) nm = nm.substr(0, lt);
     ProfSum *slot = nullptr;
