@@ -127,8 +127,12 @@ k_syndrome(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32
 // polynomial basis.  The whole codeword of a slab sits in shared memory as plane words
 // (padded: word p + p/32); work item = (class, chunk of lc = ceil(order/32) consecutive e), the 32
 // lanes of a warp are the 32 chunks of one class; a chunk's remainder is shifted by x^(q lc) with
-// the fold constants (shared by all classes).  grid = slabs; dynamic smem =
-// (ceil(order / 32) * 33 + nodd * M) words.
+// the fold constants.  Bank conflicts: the lanes of a warp read positions that differ by multiples
+// of D = lc j^-1 and all move by the same step, so the conflict pattern is a property of (j, lc).
+// The host picks, per class, the chunk length lc and the conjugate j' = j 2^i to work with
+// (S_j = S_j'^(2^(M-i)); the Frobenius power is GF(2)-linear, so it is folded into the fold
+// constants at no cost) that minimise the simulated number of shared-memory wavefronts.
+// grid = slabs; dynamic smem = (ceil(order / 32) * 33 + nodd * M) words.
 template <int M>
 __device__ __forceinline__ void lfsr_field_step(uint32_t (&s)[M], uint32_t in)
 {
@@ -142,7 +146,7 @@ __device__ __forceinline__ void lfsr_field_step(uint32_t (&s)[M], uint32_t in)
 template <int M>
 __global__ void __launch_bounds__(BCHFFT_NT_SYN, BCHFFT_MINB_SYNP)
 k_syndrome_p(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32_t length_bits,
-             uint32_t batch, uint32_t nodd, uint32_t lc, const uint32_t *__restrict__ jinv,
+             uint32_t batch, uint32_t nodd, const uint32_t *__restrict__ lcs, const uint32_t *__restrict__ jinv,
              const uint32_t *__restrict__ start_idx, const uint32_t *__restrict__ foldp,
              const uint32_t *__restrict__ vbits, uint32_t *__restrict__ acc, uint32_t *__restrict__ parity)
 {
@@ -185,9 +189,9 @@ k_syndrome_p(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint
   __syncthreads();
 
   // phase B
-  const uint32_t main_steps = lc > 32u ? ((lc - 32u) & ~7u) : 0u;
   for (uint32_t item = threadIdx.x; item < nodd * 32u; item += blockDim.x) {
     const uint32_t ji = item >> 5, q = item & 31u;
+    const uint32_t lc = lcs[ji];
     const uint32_t e0 = q * lc, e1 = (e0 + lc < order) ? e0 + lc : order;   // chunk [e0, e1)
     const uint32_t nsteps = e1 > e0 ? e1 - e0 : 0u;
     const uint32_t step = jinv[ji];
@@ -196,24 +200,23 @@ k_syndrome_p(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint
 #pragma unroll
     for (int b = 0; b < M; ++b) s[b] = 0u;
     // descending e: s <- s X + c_(p(e));  p(e - 1) = p(e) - j^-1 mod order
-    const uint32_t pro = nsteps > main_steps ? nsteps - main_steps : 0u;
+    // (all chunks of a class but the last have the same length, so the trip counts are warp-uniform)
+    const uint32_t main_steps = nsteps & ~7u, pro = nsteps - main_steps;
     for (uint32_t k = 0; k < pro; ++k) {
       lfsr_field_step<M>(s, planes[idx + (idx >> 5)]);
       const uint32_t t = idx - step, t2 = t + order;
       idx = t < t2 ? t : t2;   // unsigned min: t wrapped around 2^32 exactly when idx < step
     }
-    if (nsteps >= main_steps) {
-      for (uint32_t k = 0; k < main_steps; k += 8u) {
+    for (uint32_t k = 0; k < main_steps; k += 8u) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          lfsr_field_step<M>(s, planes[idx + (idx >> 5)]);
-          const uint32_t t = idx - step, t2 = t + order;
-          idx = t < t2 ? t : t2;
-        }
+      for (int u = 0; u < 8; ++u) {
+        lfsr_field_step<M>(s, planes[idx + (idx >> 5)]);
+        const uint32_t t = idx - step, t2 = t + order;
+        idx = t < t2 ? t : t2;
       }
     }
     // shift by x^(q lc): out = sum_b s[b] * x^(q lc + b)
-    const uint32_t *fc = foldp + q * M;
+    const uint32_t *fc = foldp + (size_t)item * M;
     uint32_t out[M];
 #pragma unroll
     for (int k = 0; k < M; ++k) out[k] = 0u;

@@ -51,6 +51,11 @@
 #ifndef BCHFFT_MINB_LOC
 #define BCHFFT_MINB_LOC 2
 #endif
+// butterfly sweeps of the FFT pass kernels use the branch-over-set-bits multiply where the
+// multiplier is warp-uniform (tile_butterfly*, UNI)
+#ifndef BCHFFT_UNI_BF
+#define BCHFFT_UNI_BF 1
+#endif
 #ifndef BCHFFT_MINB_SYNP
 #define BCHFFT_MINB_SYNP 3
 #endif

@@ -17,8 +17,8 @@ struct bchfft_code {
   // universal-LFSR syndrome kernel (k_syndrome_p): usable when every odd j < d is coprime to the
   // field order; per class j^-1 mod order, per (class, chunk) the first permuted position, per
   // chunk the shift constants x^(q lc + b)
-  uint32_t syn_p = 0, syn_lc = 0;
-  uint32_t *d_jinv = nullptr, *d_start = nullptr, *d_foldp = nullptr;
+  uint32_t syn_p = 0;
+  uint32_t *d_jinv = nullptr, *d_start = nullptr, *d_foldp = nullptr, *d_lcs = nullptr;
   // work sets: [0] serves the device-pointer and stage-level entry points, [1] .. [3] are the
   // lanes of the pipelined host entry point (copy-in / decode / copy-out overlap)
   struct WorkSet {
@@ -126,7 +126,7 @@ static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, 
     const size_t smem_p = sizeof(uint32_t) * ((size_t)((c->f->order + 31u) / 32u) * 33u + (size_t)c->nodd * M);
     BCHFFT_ENSURE_SMEM(k_syndrome_p<M>, c->f->device, smem_p);
     BCHFFT_RUN(k_syndrome_p<M>, dim3(ns), dim3(kNtSyn), smem_p, st, (const uint32_t *)d_words, c->wpc * 2u,
-               c->length, (uint32_t)cnt, c->nodd, c->syn_lc, (const uint32_t *)c->d_jinv,
+               c->length, (uint32_t)cnt, c->nodd, (const uint32_t *)c->d_lcs, (const uint32_t *)c->d_jinv,
                (const uint32_t *)c->d_start, (const uint32_t *)c->d_foldp, (const uint32_t *)c->d_vbits,
                s.acc, s.parity);
     BCHFFT_RUN(k_syn_finish<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
@@ -427,26 +427,71 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
     for (uint32_t ji = 0; ji < c->nodd && ok; ji++) ok = gcd((2u * ji + 1u) % order, order) == 1u;
     const size_t smem_p = sizeof(uint32_t) * ((size_t)((order + 31u) / 32u) * 33u + (size_t)c->nodd * M);
     if (ok && smem_p <= (size_t)200 * 1024) {
-      const uint32_t lc = (order + 31u) / 32u;
-      std::vector<uint32_t> jinv(c->nodd), start((size_t)c->nodd * 32u), foldp((size_t)32 * M);
-      for (uint32_t ji = 0; ji < c->nodd; ji++) {
-        const uint32_t j = (2u * ji + 1u) % order;
-        // j^-1 mod order by the extended Euclid
-        int64_t a = j, b = order, x0 = 1, x1 = 0;
+      const uint32_t lc_min = (order + 31u) / 32u, lc_max = lc_min + lc_min / 8u;
+      auto inverse = [&](uint32_t v) -> uint32_t {   // v^-1 mod order by the extended Euclid
+        int64_t a = v, b = order, x0 = 1, x1 = 0;
         while (b) { const int64_t qq = a / b, r = a % b; a = b; b = r; const int64_t x2 = x0 - qq * x1; x0 = x1; x1 = x2; }
-        const uint32_t inv = (uint32_t)(((x0 % (int64_t)order) + order) % order);
-        jinv[ji] = inv;
+        return (uint32_t)(((x0 % (int64_t)order) + order) % order);
+      };
+      // shared-memory wavefronts of the 32 lanes' reads, sampled every 4th step
+      auto cost = [&](uint32_t inv, uint32_t lc) -> uint64_t {
+        uint32_t idx[32], n[32];
+        uint32_t longest = 0;
         for (uint32_t q = 0; q < 32u; q++) {
           const uint64_t e0 = (uint64_t)q * lc, e1 = e0 + lc < order ? e0 + lc : order;
-          start[(size_t)ji * 32u + q] = e1 > e0 ? (uint32_t)(((e1 - 1u) * (uint64_t)inv) % order) : 0u;
+          n[q] = e1 > e0 ? (uint32_t)(e1 - e0) : 0u;
+          idx[q] = n[q] ? (uint32_t)(((e1 - 1u) * (uint64_t)inv) % order) : 0u;
+          if (n[q] > longest) longest = n[q];
+        }
+        const uint32_t step4 = (uint32_t)(((uint64_t)inv * 4u) % order);
+        uint64_t total = 0;
+        for (uint32_t k = 0; k < longest; k += 4u) {
+          uint8_t load[32] = {0};
+          uint32_t worst = 1;
+          for (uint32_t q = 0; q < 32u; q++) {
+            if (k >= n[q]) continue;
+            const uint32_t bank = (idx[q] + (idx[q] >> 5)) & 31u;
+            if (++load[bank] > worst) worst = load[bank];
+            idx[q] = idx[q] >= step4 ? idx[q] - step4 : idx[q] + order - step4;
+          }
+          total += worst;
+        }
+        return total;
+      };
+      std::vector<uint32_t> jinv(c->nodd), lcs(c->nodd), start((size_t)c->nodd * 32u), foldp((size_t)c->nodd * 32u * M);
+      for (uint32_t ji = 0; ji < c->nodd; ji++) {
+        const uint32_t j = (2u * ji + 1u) % order;
+        uint64_t best = ~0ull;
+        uint32_t best_i = 0, best_lc = lc_min, best_inv = inverse(j);
+        uint32_t jc = j;   // conjugate j 2^i
+        for (uint32_t i = 0; i < M; i++, jc = (uint32_t)(((uint64_t)jc * 2u) % order)) {
+          const uint32_t inv = inverse(jc);
+          for (uint32_t lc = lc_min; lc <= lc_max; lc++) {
+            // idle lanes (chunks beyond the end) are lost throughput: charge them like wavefronts
+            const uint64_t cst = cost(inv, lc) * 32u * lc / order;
+            if (cst < best) { best = cst; best_i = i; best_lc = lc; best_inv = inv; }
+          }
+          if (i > 0 && jc == j) break;   // short orbit
+        }
+        jinv[ji] = best_inv;
+        lcs[ji] = best_lc;
+        // S_j = S_(j 2^i)^(2^(M-i)): raise the fold constants to that power (exponents times 2^(M-i))
+        const uint32_t fpow = (M - best_i) % M;
+        for (uint32_t q = 0; q < 32u; q++) {
+          const uint64_t e0 = (uint64_t)q * best_lc, e1 = e0 + best_lc < order ? e0 + best_lc : order;
+          start[(size_t)ji * 32u + q] = e1 > e0 ? (uint32_t)(((e1 - 1u) * (uint64_t)best_inv) % order) : 0u;
+          for (uint32_t b = 0; b < M; b++) {
+            uint64_t ex = ((uint64_t)q * best_lc + b) % order;
+            for (uint32_t r = 0; r < fpow; r++) ex = (ex * 2u) % order;
+            foldp[((size_t)ji * 32u + q) * M + b] = f->h_exp[ex];
+          }
         }
       }
-      for (uint32_t q = 0; q < 32u; q++)
-        for (uint32_t b = 0; b < M; b++) foldp[(size_t)q * M + b] = f->h_exp[((uint64_t)q * lc + b) % order];
       cudaError_t p0 = cudaMalloc((void **)&c->d_jinv, jinv.size() * 4 + 16);
       cudaError_t p1 = cudaMalloc((void **)&c->d_start, start.size() * 4 + 16);
       cudaError_t p2 = cudaMalloc((void **)&c->d_foldp, foldp.size() * 4 + 16);
-      if (p0 != cudaSuccess || p1 != cudaSuccess || p2 != cudaSuccess) {
+      cudaError_t p3 = cudaMalloc((void **)&c->d_lcs, lcs.size() * 4 + 16);
+      if (p0 != cudaSuccess || p1 != cudaSuccess || p2 != cudaSuccess || p3 != cudaSuccess) {
         set_error("bchfft_code_create: cudaMalloc failed");
         bchfft_code_destroy(c);
         return BCHFFT_ERR_CUDA;
@@ -454,7 +499,7 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
       cudaMemcpy(c->d_jinv, jinv.data(), jinv.size() * 4, cudaMemcpyHostToDevice);
       cudaMemcpy(c->d_start, start.data(), start.size() * 4, cudaMemcpyHostToDevice);
       cudaMemcpy(c->d_foldp, foldp.data(), foldp.size() * 4, cudaMemcpyHostToDevice);
-      c->syn_lc = lc;
+      cudaMemcpy(c->d_lcs, lcs.data(), lcs.size() * 4, cudaMemcpyHostToDevice);
       c->syn_p = 1u;
     }
   }
@@ -473,6 +518,7 @@ extern "C" void bchfft_code_destroy(bchfft_code *c)
   cudaFree(c->d_jinv);
   cudaFree(c->d_start);
   cudaFree(c->d_foldp);
+  cudaFree(c->d_lcs);
   for (auto &w : c->work) {
     w.scratch.release();
     w.fwd_buf.release();

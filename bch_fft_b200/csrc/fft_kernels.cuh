@@ -614,11 +614,15 @@ __device__ __forceinline__ uint32_t taylor_run(const PassDesc &desc, const TileG
 }
 
 // BF(d): lo' = lo + gam[d][p >> (d+1)] * hi ; hi' = lo' + hi
-template <int M, class Epi>
+// UNI: when the butterfly bit sits above local bit 4 the 32 lanes of a warp (local bits 0..4)
+// belong to one block, i.e. share the multiplier: it is warp-uniform and the multiply branches
+// over its set bits (bs_mad_uniform) instead of masking all M*M partial products.
+template <int M, class Epi, bool UNI = false>
 __device__ __forceinline__ void tile_butterfly(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
                                                const uint32_t *__restrict__ gam_d, uint32_t d, uint32_t lbd,
                                                const Epi *epi)
 {
+  const bool uni = UNI && lbd >= 5u;
   const SweepMap map = make_sweep_map(t, lbd, 1);
   const uint32_t o = 1u << lbd;
   for (uint32_t j = threadIdx.x; j < (T >> 1); j += blockDim.x) {
@@ -631,7 +635,11 @@ __device__ __forceinline__ void tile_butterfly(uint32_t *S, uint32_t T, uint32_t
       lo[b] = S[b * T + s0];
       hi[b] = S[b * T + s1];
     }
-    if (G) bs_mad_scalar<M>(lo, hi, G);
+    if (UNI && uni) {
+      if (G) bs_mad_uniform<M>(lo, hi, G);
+    } else if (G) {
+      bs_mad_scalar<M>(lo, hi, G);
+    }
 #pragma unroll
     for (int b = 0; b < M; ++b) hi[b] ^= lo[b];
     if (epi) {
@@ -648,12 +656,13 @@ __device__ __forceinline__ void tile_butterfly(uint32_t *S, uint32_t T, uint32_t
 }
 
 // BF(d) then BF(d-1) on four positions held in registers (local bits lb, lb+1 = bits d-1, d)
-template <int M, class Epi>
+template <int M, class Epi, bool UNI = false>
 __device__ __forceinline__ void tile_butterfly_r4(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
                                                   const uint32_t *__restrict__ gam_d,
                                                   const uint32_t *__restrict__ gam_dm1, uint32_t d,
                                                   uint32_t lb, const Epi *epi)
 {
+  const bool uni = UNI && lb >= 5u;
   const SweepMap map = make_sweep_map(t, lb, 2);
   for (uint32_t j = threadIdx.x; j < (T >> 2); j += blockDim.x) {
     const uint32_t l = map.pos(j);
@@ -668,7 +677,12 @@ __device__ __forceinline__ void tile_butterfly_r4(uint32_t *S, uint32_t T, uint3
       e3[b] = S[b * T + s3];
     }
     const uint32_t G = gam_d[p0 >> (d + 1)];
-    if (G) {
+    if (UNI && uni) {
+      if (G) {
+        bs_mad_uniform<M>(e0, e2, G);
+        bs_mad_uniform<M>(e1, e3, G);
+      }
+    } else if (G) {
       bs_mad_scalar<M>(e0, e2, G);
       bs_mad_scalar<M>(e1, e3, G);
     }
@@ -678,8 +692,13 @@ __device__ __forceinline__ void tile_butterfly_r4(uint32_t *S, uint32_t T, uint3
       e3[b] ^= e1[b];
     }
     const uint32_t Ga = gam_dm1[p0 >> d], Gb = gam_dm1[(p0 >> d) + 1u];
-    if (Ga) bs_mad_scalar<M>(e0, e1, Ga);
-    if (Gb) bs_mad_scalar<M>(e2, e3, Gb);
+    if (UNI && uni) {
+      if (Ga) bs_mad_uniform<M>(e0, e1, Ga);
+      if (Gb) bs_mad_uniform<M>(e2, e3, Gb);
+    } else {
+      if (Ga) bs_mad_scalar<M>(e0, e1, Ga);
+      if (Gb) bs_mad_scalar<M>(e2, e3, Gb);
+    }
 #pragma unroll
     for (int b = 0; b < M; ++b) {
       e1[b] ^= e0[b];
@@ -705,7 +724,7 @@ __device__ __forceinline__ void tile_butterfly_r4(uint32_t *S, uint32_t T, uint3
 // Runs the ops of a pass on a tile.  Consecutive Taylor levels of one depth on adjacent bits are
 // fused five at a time, consecutive butterfly levels two at a time (register-resident radix
 // blocks): fewer shared-memory round trips and barriers than one sweep per level.
-template <int M, class Epi = NoEpilogue, bool WITH_TX = false>
+template <int M, class Epi = NoEpilogue, bool WITH_TX = false, bool UNI = false>
 __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t, const TileGeom &g,
                                              const FftTables &tab, const PassDesc &desc,
                                              const Epi *epi = nullptr)
@@ -732,11 +751,11 @@ __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t
       }
       // the epilogue, if any, replaces the write-back of the pass's final sweep
       if (pair) {
-        tile_butterfly_r4<M, Epi>(S, T, t, g, tab.gam + tab.gam_off[op.d], tab.gam + tab.gam_off[op.d - 1u],
+        tile_butterfly_r4<M, Epi, UNI>(S, T, t, g, tab.gam + tab.gam_off[op.d], tab.gam + tab.gam_off[op.d - 1u],
                                   op.d, g.local_bit(op.d) - 1u, (i + 2 == desc.nops) ? epi : nullptr);
         i += 2;
       } else {
-        tile_butterfly<M, Epi>(S, T, t, g, tab.gam + tab.gam_off[op.d], op.d, g.local_bit(op.d),
+        tile_butterfly<M, Epi, UNI>(S, T, t, g, tab.gam + tab.gam_off[op.d], op.d, g.local_bit(op.d),
                                (i + 1 == desc.nops) ? epi : nullptr);
         i += 1;
       }
@@ -758,7 +777,7 @@ k_gm_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t s
   BCHFFT_MARK(1);
   tile_load<M>(S, T, src + (size_t)blockIdx.y * src_slab_words, g, desc.src_mask);
   __syncthreads();
-  tile_run_ops<M>(S, T, desc.t, g, tab, desc);
+  tile_run_ops<M, NoEpilogue, false, (BCHFFT_UNI_BF != 0 && M >= 13)>(S, T, desc.t, g, tab, desc);
   BCHFFT_MARK(2);
   tile_store<M>(S, T, dst + (size_t)blockIdx.y * dst_slab_words, g);
   BCHFFT_MARK(3);
@@ -909,7 +928,7 @@ k_gm_pass_pm(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_
   const TileGeom g = tile_geom(desc, blockIdx.x);
   tile_load_pm<M>(S, desc.t, src + (size_t)blockIdx.y * slab_words, nbits, g);
   __syncthreads();
-  tile_run_ops<M, NoEpilogue, true>(S, T, desc.t, g, tab, desc);
+  tile_run_ops<M, NoEpilogue, true, (BCHFFT_UNI_BF != 0)>(S, T, desc.t, g, tab, desc);
   if (dst_em) tile_store<M>(S, T, dst + (size_t)blockIdx.y * slab_words, g);
   else tile_store_pm<M>(S, desc.t, dst + (size_t)blockIdx.y * slab_words, nbits, g);
 }

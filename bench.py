@@ -414,9 +414,10 @@ def run_fft(args, rank, world, local_rank, lib, host, peak_gbs, peak_src, barrie
     ksum = sum(ms for ms, _ in prof.values()) or 1.0
     top = max(prof, key=lambda k: prof[k][0])
     top_ms, top_n = prof[top]
-    # k_gm_pass is launched once per pass and per chunk of slabs: one launch covers Bf*n/chunks points
-    passes = max(1, top_n)
-    points_per_launch = Bf * n / passes
+    # every pass kernel is launched once per pass and per chunk of slabs; k_bitslice_in runs exactly
+    # once per chunk, so one launch of the dominant kernel covers Bf * n / chunks points
+    chunks = max(1, prof.get("k_bitslice_in", (0.0, 1))[1])
+    points_per_launch = Bf * n / chunks
     achieved = points_per_launch * bytes_per_point / (top_ms / top_n * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": measured_traffic(top, points_per_launch),
