@@ -33,6 +33,8 @@ _SIGNATURES = {
     "bchfft_code_destroy": (None, [_vp]),
     "bchfft_bch_decode_host": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "bchfft_bch_decode_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "bchfft_bch_encode_host": (C.c_int, [_vp, _vp, _sz, _u32, _vp, _sz]),
+    "bchfft_bch_encode_dev": (C.c_int, [_vp, _vp, _sz, _u32, _vp, _sz, _vp]),
     "bchfft_bch_syndrome_host": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "bchfft_bch_elp_host": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "bchfft_bch_locate_host": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp]),

@@ -102,6 +102,8 @@ class Host:
         L.bch_decode.argtypes = [cp, ulp, bp, u32p]
         L.bch_decode_batch.restype = C.c_int
         L.bch_decode_batch.argtypes = [cp, ulp, C.c_size_t, C.POINTER(C.c_ubyte), u32p]
+        L.bch_encode_batch.restype = C.c_int
+        L.bch_encode_batch.argtypes = [cp, ulp, ulp, C.c_size_t, C.c_uint32, C.c_size_t]
         L.bchfft_last_error.restype = C.c_char_p
         L.bchfft_host_shutdown.restype = None
 
@@ -214,6 +216,17 @@ class BchCode:
         if self.host.lib.bch_encode(C.byref(self.c), cw.ctypes.data_as(ulp), bp, bits.size):
             raise ValueError("too many data bits")
         return cw
+
+    def encode_batch(self, packed_data, data_bits: int) -> np.ndarray:
+        """bch_encode_batch: packed_data [B, data_words] uint64 (bit k of an item = bit k % 64 of
+        word k // 64) -> codewords [B, W]"""
+        d = np.ascontiguousarray(packed_data, np.uint64)
+        d = d.reshape(-1, d.shape[-1])
+        out = np.zeros((d.shape[0], self.words), np.uint64)
+        self.host._check(self.host.lib.bch_encode_batch(
+            C.byref(self.c), out.ctypes.data_as(ulp), d.ctypes.data_as(ulp), d.shape[1], data_bits,
+            d.shape[0]), "bch_encode_batch")
+        return out
 
     def buffers(self):
         if self._buf is None:

@@ -842,6 +842,78 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
   locu_flush(queue, &s_qn, glist, errloc, count, positions, pos_stride);
 }
 
+
+// ---- systematic encoder (bch.c:492-506) -------------------------------------
+// codeword = data * X^dg + (data * X^dg mod g): data bit i -> codeword bit i + dg, parity in bits
+// 0 .. dg-1.  One thread per codeword, byte-wise division by g: R <- (R << 8) ^ T[top byte of R ^
+// data byte], T[v] = v(X) X^dg mod g (256 rows of NW 64-bit words, staged in shared memory by the
+// CTA; dynamic smem = 256 * NW * 8 bytes).  Requires 8 <= dg <= 64 NW.  data: [batch][dwords]
+// packed data bits (bit i of item = bit i % 64 of word i / 64), only the first data_bits count.
+template <int NW>
+__global__ void __launch_bounds__(128)
+k_encode(const uint64_t *__restrict__ data, uint32_t dwords, uint32_t data_bits, uint32_t dg,
+         const uint64_t *__restrict__ table, uint64_t *__restrict__ cw_out, uint32_t wpc, uint32_t batch)
+{
+  BCHFFT_DYN_SMEM(uint64_t, T);
+  for (uint32_t i = threadIdx.x; i < 256u * NW; i += blockDim.x) T[i] = table[i];
+  __syncthreads();
+  const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cw >= batch) return;
+  const uint64_t *dsrc = data + (size_t)cw * dwords;
+  uint64_t R[NW];
+#pragma unroll
+  for (int k = 0; k < NW; ++k) R[k] = 0ull;
+  const uint32_t tw = (dg - 8u) >> 6, tsh = (dg - 8u) & 63u;   // top byte of R = bits dg-8 .. dg-1
+  const uint32_t hw = (dg - 1u) >> 6;                           // last word of R in use
+  const uint64_t hmask = (dg & 63u) ? ((1ull << (dg & 63u)) - 1ull) : ~0ull;
+  const uint32_t nbytes = (data_bits + 7u) >> 3;
+  for (uint32_t b = nbytes; b-- > 0;) {
+    uint64_t dw = dsrc[b >> 3];
+    const uint32_t last = data_bits - 1u;
+    if ((b >> 3) == (last >> 6) && (last & 63u) != 63u) dw &= (2ull << (last & 63u)) - 1ull;   // bits >= data_bits
+    const uint32_t dbyte = (uint32_t)(dw >> ((b & 7u) * 8u)) & 255u;
+    uint32_t top = 0u;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      if ((uint32_t)k == tw) top |= (uint32_t)(R[k] >> tsh);
+      if ((uint32_t)k == tw + 1u && tsh > 56u) top |= (uint32_t)(R[k] << (64u - tsh));
+    }
+    const uint64_t *row = T + (size_t)((top ^ dbyte) & 255u) * NW;
+#pragma unroll
+    for (int k = NW - 1; k >= 0; --k) {
+      const uint64_t lo = k > 0 ? (R[k - 1] >> 56) : 0ull;
+      R[k] = ((R[k] << 8) | lo) ^ row[k];
+    }
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      if ((uint32_t)k == hw) R[k] &= hmask;
+      if ((uint32_t)k > hw) R[k] = 0ull;
+    }
+  }
+  // codeword words: parity | data shifted up by dg
+  uint64_t *out = cw_out + (size_t)cw * wpc;
+  const uint32_t sw = dg >> 6, sh = dg & 63u;
+  const uint32_t lastd = data_bits ? (data_bits - 1u) >> 6 : 0u;
+  for (uint32_t j = 0; j < wpc; ++j) {
+    uint64_t v = 0ull;
+#pragma unroll
+    for (int k = 0; k < NW; ++k)
+      if ((uint32_t)k == j) v = R[k];
+    if (data_bits && j >= sw) {
+      const uint32_t i = j - sw;
+      auto dword = [&](uint32_t w) -> uint64_t {
+        if (w > lastd) return 0ull;
+        uint64_t x = dsrc[w];
+        if (w == lastd && ((data_bits - 1u) & 63u) != 63u) x &= (2ull << ((data_bits - 1u) & 63u)) - 1ull;
+        return x;
+      };
+      v |= dword(i) << sh;
+      if (sh && i >= 1u) v |= dword(i - 1u) >> (64u - sh);
+    }
+    out[j] = v;
+  }
+}
+
 // ---- verdict + correction (bch.c:531-561) ---------------------------------------------------
 // ok = 1, corrected = 0 for a clean word; L > t -> ok = 0, corrected = 0; otherwise corrected =
 // #roots and the bits are flipped iff #roots == L.  Flips outside the packed array (only

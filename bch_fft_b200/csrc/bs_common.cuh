@@ -53,6 +53,10 @@
 #endif
 // butterfly sweeps of the FFT pass kernels use the branch-over-set-bits multiply where the
 // multiplier is warp-uniform (tile_butterfly*, UNI)
+// radix-4 butterfly sweeps (two levels per shared-memory round trip, four elements in registers)
+#ifndef BCHFFT_BF_R4
+#define BCHFFT_BF_R4 1
+#endif
 #ifndef BCHFFT_UNI_BF
 #define BCHFFT_UNI_BF 1
 #endif

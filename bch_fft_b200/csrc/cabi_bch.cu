@@ -18,6 +18,9 @@ struct bchfft_code {
   // field order; per class j^-1 mod order, per (class, chunk) the first permuted position, per
   // chunk the shift constants x^(q lc + b)
   uint32_t syn_p = 0;
+  // systematic encoder (k_encode): T[v] = v(X) X^deg(g) mod g, 256 rows of enc_nw 64-bit words
+  uint32_t enc_nw = 0;
+  uint64_t *d_enc_table = nullptr;
   uint32_t *d_jinv = nullptr, *d_start = nullptr, *d_foldp = nullptr, *d_lcs = nullptr;
   // work sets: [0] serves the device-pointer and stage-level entry points, [1] .. [3] are the
   // lanes of the pipelined host entry point (copy-in / decode / copy-out overlap)
@@ -503,6 +506,38 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
       c->syn_p = 1u;
     }
   }
+  // encoder table (needs the generator polynomial; degree 8 .. 2048)
+  if (packed_gen_poly && gen_poly_degree >= 8u && gen_poly_degree <= 2048u && gen_poly_degree < length) {
+    const uint32_t dg = gen_poly_degree, gw = (dg >> 6) + 1u;
+    uint32_t nw = 1;
+    while (nw * 64u < dg) nw *= 2u;
+    std::vector<uint64_t> table((size_t)256 * nw, 0ull), r(gw + 1u);
+    for (uint32_t v = 0; v < 256u; v++) {
+      // r = v(X) X^dg mod g: feed the 8 bits of v (highest first) through the division by g
+      std::fill(r.begin(), r.end(), 0ull);
+      for (int bit = 7; bit >= 0; bit--) {
+        const uint32_t fb = (uint32_t)((r[(dg - 1u) >> 6] >> ((dg - 1u) & 63u)) & 1ull) ^ ((v >> bit) & 1u);
+        uint64_t carry = 0;
+        for (uint32_t k = 0; k < gw; k++) {
+          const uint64_t nc = r[k] >> 63;
+          r[k] = (r[k] << 1) | carry;
+          carry = nc;
+        }
+        r[dg >> 6] &= ~(1ull << (dg & 63u));                   // drop the bit shifted out of degree dg-1
+        if (fb)
+          for (uint32_t k = 0; k < gw; k++) r[k] ^= packed_gen_poly[k];
+        r[dg >> 6] &= (dg & 63u) ? ((1ull << (dg & 63u)) - 1ull) : 0ull;   // g's leading coefficient
+      }
+      for (uint32_t k = 0; k < nw && k < gw; k++) table[(size_t)v * nw + k] = r[k];
+    }
+    if (cudaMalloc((void **)&c->d_enc_table, table.size() * 8 + 16) != cudaSuccess) {
+      set_error("bchfft_code_create: cudaMalloc failed");
+      bchfft_code_destroy(c);
+      return BCHFFT_ERR_CUDA;
+    }
+    cudaMemcpy(c->d_enc_table, table.data(), table.size() * 8, cudaMemcpyHostToDevice);
+    c->enc_nw = nw;
+  }
   *out = c;
   return BCHFFT_OK;
 }
@@ -519,6 +554,7 @@ extern "C" void bchfft_code_destroy(bchfft_code *c)
   cudaFree(c->d_start);
   cudaFree(c->d_foldp);
   cudaFree(c->d_lcs);
+  cudaFree(c->d_enc_table);
   for (auto &w : c->work) {
     w.scratch.release();
     w.fwd_buf.release();
@@ -606,6 +642,92 @@ extern "C" int bchfft_bch_decode_host(bchfft_code *c, uint64_t *words, size_t ba
 #define X(M) case M: return decode_host_run<M>(c, words, batch, ok, corrected);
   BCHFFT_DISPATCH_M(c->f->m, X)
 #undef X
+}
+
+// ---- encoder ------------------------------------------------------------------------------------
+static int encode_launch(bchfft_code *c, const uint64_t *d_data, uint32_t dwords, uint32_t data_bits,
+                         uint64_t *d_cw, size_t batch, cudaStream_t st)
+{
+  const size_t smem = (size_t)256 * c->enc_nw * 8;
+  const dim3 grid((unsigned)((batch + 127) / 128)), block(128);
+#define ENC(NW)                                                                                        \
+  case NW:                                                                                             \
+    BCHFFT_ENSURE_SMEM(k_encode<NW>, c->f->device, smem);                                              \
+    BCHFFT_RUN(k_encode<NW>, grid, block, smem, st, d_data, dwords, data_bits, c->gen_degree,          \
+               (const uint64_t *)c->d_enc_table, d_cw, c->wpc, (uint32_t)batch);                       \
+    break;
+  switch (c->enc_nw) {
+    ENC(1) ENC(2) ENC(4) ENC(8) ENC(16) ENC(32)
+    default:
+      set_error("bch encode: no encoder table for this code");
+      return BCHFFT_ERR_UNSUPPORTED;
+  }
+#undef ENC
+  return BCHFFT_OK;
+}
+
+static int encode_check(bchfft_code *c, const void *data, const void *cw, uint32_t data_bits, const char *who)
+{
+  if (!c || !data || !cw) {
+    set_error("%s: null argument", who);
+    return BCHFFT_ERR_ARG;
+  }
+  if (!c->enc_nw) {
+    set_error("%s: the code context has no encoder (generator polynomial missing, or its degree is outside 8..2048)", who);
+    return BCHFFT_ERR_UNSUPPORTED;
+  }
+  if (data_bits > c->length - c->gen_degree) {   // bch.c:495
+    set_error("%s: %u data bits do not fit a codeword of %u bits with %u parity bits", who, data_bits,
+              c->length, c->gen_degree);
+    return BCHFFT_ERR_ARG;
+  }
+  return BCHFFT_OK;
+}
+
+extern "C" int bchfft_bch_encode_dev(bchfft_code *c, const uint64_t *d_data, size_t data_words,
+                                     uint32_t data_bits, uint64_t *d_codewords, size_t batch, void *stream)
+{
+  int rc = encode_check(c, d_data, d_codewords, data_bits, "bchfft_bch_encode_dev");
+  if (rc) return rc;
+  if (batch == 0) return BCHFFT_OK;
+  if (data_words * 64u < data_bits) {
+    set_error("bchfft_bch_encode_dev: data_words too small for data_bits");
+    return BCHFFT_ERR_ARG;
+  }
+  BCHFFT_CUDA_TRY(cudaSetDevice(c->f->device));
+  return encode_launch(c, d_data, (uint32_t)data_words, data_bits, d_codewords, batch,
+                       stream ? (cudaStream_t)stream : c->f->stream);
+}
+
+extern "C" int bchfft_bch_encode_host(bchfft_code *c, const uint64_t *data, size_t data_words,
+                                      uint32_t data_bits, uint64_t *codewords, size_t batch)
+{
+  int rc = encode_check(c, data, codewords, data_bits, "bchfft_bch_encode_host");
+  if (rc) return rc;
+  if (batch == 0) return BCHFFT_OK;
+  if (data_words * 64u < data_bits) {
+    set_error("bchfft_bch_encode_host: data_words too small for data_bits");
+    return BCHFFT_ERR_ARG;
+  }
+  BCHFFT_CUDA_TRY(cudaSetDevice(c->f->device));
+  cudaStream_t st = c->f->stream;
+  const size_t cw_bytes = (size_t)c->wpc * 8, d_bytes = data_words * 8;
+  size_t per = ((size_t)64 << 20) / (cw_bytes + d_bytes);
+  if (per < 1) per = 1;
+  if (per > batch) per = batch;
+  bchfft_code::WorkSet &w = c->work[0];
+  if ((rc = w.words.reserve(per * cw_bytes))) return rc;
+  if ((rc = w.scratch.reserve(per * d_bytes))) return rc;
+  for (size_t i0 = 0; i0 < batch; i0 += per) {
+    const size_t cnt = batch - i0 < per ? batch - i0 : per;
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(w.scratch.p, data + i0 * data_words, cnt * d_bytes, cudaMemcpyHostToDevice, st));
+    if ((rc = encode_launch(c, (const uint64_t *)w.scratch.p, (uint32_t)data_words, data_bits,
+                            (uint64_t *)w.words.p, cnt, st)))
+      return rc;
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(codewords + i0 * c->wpc, w.words.p, cnt * cw_bytes, cudaMemcpyDeviceToHost, st));
+    BCHFFT_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return BCHFFT_OK;
 }
 
 // ---- stage-level entry points ---------------------------------------------------------------

@@ -745,7 +745,7 @@ __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t
       if constexpr (WITH_TX) i += tile_tx_sweep(S, T, t, g, desc, i, (uint32_t)M);
     } else {
       bool pair = false;
-      if (M <= 16 && i + 1 < desc.nops) {
+      if (BCHFFT_BF_R4 && M <= 16 && i + 1 < desc.nops) {
         const PassOp nx = desc.ops[i + 1];
         pair = nx.type == OP_BF && nx.d + 1u == op.d && g.local_bit(nx.d) + 1u == g.local_bit(op.d);
       }

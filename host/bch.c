@@ -266,3 +266,16 @@ int bch_decode_batch(TbchCode* p_code, unsigned long* pio_words, size_t p_count,
   bchfft_host_unlock();
   return status;
 }
+
+int bch_encode_batch(TbchCode* p_code, unsigned long* po_codewords, const unsigned long* p_data,
+                     size_t p_data_words, uint32_t p_data_bits, size_t p_count)
+{
+  int status = 0;
+  bchfft_host_lock();
+  bchfft_code* ctx = bchfft_host_code(p_code, &status);
+  if (ctx)
+    status = bchfft_bch_encode_host(ctx, (const uint64_t*) p_data, p_data_words, p_data_bits,
+                                    (uint64_t*) po_codewords, p_count);
+  bchfft_host_unlock();
+  return status;
+}

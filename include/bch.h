@@ -57,6 +57,13 @@ void bch_free_buffers(TbchCodeBuffers* p_buffer);
 int bch_decode_batch(TbchCode* p_code, unsigned long* pio_words, size_t p_count,
                      unsigned char* po_ok, uint32_t* po_corrected);
 
+/* Batched systematic encoder: word i of po_codewords ([p_count][W], W = words per codeword) is what
+ * bch_encode writes for the data bits of item i, given packed: p_data is [p_count][p_data_words],
+ * bit k of an item = bit k % 64 of word k / 64, p_data_bits bits per item.  Returns 0, or a negative
+ * bchfft status (too many data bits, generator degree outside what the device encoder supports). */
+int bch_encode_batch(TbchCode* p_code, unsigned long* po_codewords, const unsigned long* p_data,
+                     size_t p_data_words, uint32_t p_data_bits, size_t p_count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,18 @@ int bchfft_bch_decode_host(bchfft_code *c, uint64_t *words, size_t batch, uint8_
 int bchfft_bch_decode_dev(bchfft_code *c, uint64_t *d_words, size_t batch, uint8_t *d_ok,
                           uint32_t *d_corrected, void *stream);
 
+/* Systematic encoder: bch_encode (include/bch.h:174-188, libbch/bch.c:492-506) run `batch` times.
+ * data: [batch][data_words] packed data bits (bit i of an item = bit i % 64 of word i / 64; only the
+ * first data_bits count, the reference's p_data[i] = that bit); codewords: [batch][words_per_cw],
+ * data bit i at codeword bit i + deg(g), parity (data X^deg(g) mod g) in bits 0 .. deg(g)-1, the
+ * rest zero.  BCHFFT_ERR_ARG when data_bits > length - deg(g) (where the reference returns 1);
+ * BCHFFT_ERR_UNSUPPORTED when the code context was created without its generator polynomial or
+ * deg(g) is outside 8..2048. */
+int bchfft_bch_encode_host(bchfft_code *c, const uint64_t *data, size_t data_words, uint32_t data_bits,
+                           uint64_t *codewords, size_t batch);
+int bchfft_bch_encode_dev(bchfft_code *c, const uint64_t *d_data, size_t data_words, uint32_t data_bits,
+                          uint64_t *d_codewords, size_t batch, void *stream);
+
 /* Stage-level entry points, for callers that drive the stages one by one like bch/main.c:103-122.
  * syndromes: [batch][distance] = c(x^i), i = 0..d-1 (bch_eval_syndrome, bch.c:228-326; entry 0
  * follows the reference's method rule: c(1) on its FFT path, (c mod g)(1) on its direct path);

@@ -39,7 +39,7 @@ def test_host_library_exports_reference_symbols():
                  "multiplicative_FFT", "evaluate_polynomial_multiplicative_FFT",
                  "create_binary_finite_field", "free_finite_field", "multiply", "multiply_by_log",
                  "square", "inverse", "get_bit", "set_bit", "add_bit", "degree_to_packed_size",
-                 "additive_fft_batch", "bch_decode_batch", "multiplicative_fft_batch"):
+                 "additive_fft_batch", "bch_decode_batch", "bch_encode_batch", "multiplicative_fft_batch"):
         assert hasattr(lib, name), name
 
 

@@ -183,6 +183,35 @@ def test_emu_host_api_decode_golden(emu_libs, rec):
         assert (o, c) == (rec["ok"][i], rec["corrected"][i]) and (w == out[i]).all()
 
 
+def _encode_cases(host, port, n, t, rng):
+    """bch_encode_batch against one bch_encode call per item (host library) and the oracle's encoder"""
+    code = host.bch_gen_code(n, 2 * t + 1)
+    pc = port.code(n, t)
+    k = code.data_bits
+    for nbits in sorted({k, k - 1, max(k - 67, 1), 1, min(64, k), min(65, k)}):
+        B = 37
+        bits = rng.integers(0, 2, (B, nbits), dtype=np.uint32)
+        bits[0] = 0
+        bits[1] = 1
+        dw = (nbits + 63) // 64
+        packed = np.zeros((B, dw), np.uint64)
+        for i in range(nbits):
+            packed[:, i // 64] |= bits[:, i].astype(np.uint64) << np.uint64(i % 64)
+        packed[:, -1] |= np.uint64(0xFFFF) << np.uint64(48) if nbits % 64 and nbits % 64 <= 48 else np.uint64(0)
+        out = code.encode_batch(packed, nbits)       # bits above data_bits in the last word are ignored
+        for b in (0, 1, 2, B - 1):
+            assert (out[b] == code.encode(bits[b])).all(), (n, t, nbits, b)
+            assert (out[b] == pc.encode(bits[b])).all(), (n, t, nbits, b)
+    with pytest.raises(Exception):
+        code.encode_batch(np.zeros((2, (k + 64) // 64 + 1), np.uint64), k + 1)     # bch.c:495
+
+
+@pytest.mark.parametrize("n,t", [(255, 8), (8191, 16), (8191, 64), (5000, 12), (1023, 10)])
+def test_emu_encode_batch(emu_libs, port, n, t):
+    _, host = emu_libs
+    _encode_cases(host, port, n, t, np.random.default_rng(n + t))
+
+
 def test_emu_host_api_additive(emu_libs, port):
     _, host = emu_libs
     f = host.create_binary_finite_field(10)

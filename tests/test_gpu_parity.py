@@ -209,51 +209,6 @@ def test_decode_full_batch_properties(gpu_libs, port):
     words, nerr = synth.corrupt_codewords(pool, n, t, B, 0xC3, beyond_fraction=0.01)
     diff = words ^ clean
     ok, corr, out = code.decode_batch(words)
-    assert [int(x) for x in ok] == rec["ok"] and [int(x) for x in corr] == rec["corrected"]
-    assert f"{fnv64(out):016x}" == rec["fnv_out"]
-    for i in (0, 1, 2, len(words) - 1):
-        o, c, w = code.decode(words[i])
-        assert (o, c) == (rec["ok"][i], rec["corrected"][i]) and (w == out[i]).all()
-
-
-def test_host_api_additive_single_call(gpu_libs, port):
-    """evaluate_polynomial_additive_FFT / additive_DFT* drop-in semantics (additive_fft.c:13-21)"""
-    _, host = gpu_libs
-    f = host.create_binary_finite_field(16)
-    poly = synth.demo_poly(16)
-    p = poly.copy()
-    got = f.evaluate_polynomial_additive_FFT(p, (1 << 16) - 1)
-    assert fnv64(got) == 0xda6143e12631d2df and fnv64(p) == 0x4ce7d70654a732f3   # Appendix C
-    rng = np.random.default_rng(4)
-    poly = rng.integers(0, 1 << 16, 1 << 16, dtype=np.uint32)
-    want_nat = port.additive_fft(16, poly, 700)[1]
-    for variant in ("additive_DFT_opt", "additive_DFT", "additive_DFT_ref"):
-        p = poly.copy()
-        assert (f.additive_DFT(p, 700, variant) == want_nat).all()
-
-
-def test_decode_full_batch_properties(gpu_libs, port):
-    """BASELINE configs[2] at full size (10^6 words, n=8191, t=16): encode -> corrupt -> decode
-    round trip.  Every word with <= t distinct errors (none at bit 0) must come back equal to its
-    clean codeword with corrected = #errors; decoding twice is idempotent; a 20000-word sample is
-    compared field by field with the oracle."""
-    _, host = gpu_libs
-    n, t, B = 8191, 16, 1_000_000
-    code = host.bch_gen_code(n, 2 * t + 1)
-    bits = (synth.splitmix64(0xC3, 64 * code.data_bits) & np.uint64(1)).astype(np.uint32)
-    pool = np.stack([code.encode(b) for b in bits.reshape(64, -1)])
-    # rebuild the same words without errors: same seed, t = 0 draws nothing
-    r = synth.splitmix64(0xC3, B * 6).reshape(B, 6)
-    clean = np.zeros((B, code.words), np.uint64)
-    for k in range(4):
-        clean ^= pool[(r[:, k] % np.uint64(64)).astype(np.int64)]
-    words, nerr = synth.corrupt_codewords(pool, n, t, B, 0xC3, beyond_fraction=0.01)
-    diff = words ^ clean
-    weight = np.zeros(B, np.int64)
-    for k in range(code.words):
-        weight += np.array([bin(int(x)).count("1") for x in diff[:20000, k]] + [0] * 0, dtype=np.int64) \
-            if False else 0
-    ok, corr, out = code.decode_batch(words)
     sample = 20000
     pc = port.code(n, t)
     rok, rcorr, rout = pc.decode_batch(words[:sample])
@@ -269,6 +224,41 @@ def test_decode_full_batch_properties(gpu_libs, port):
     assert (out[ok == 0] == words[ok == 0]).all()            # failures leave the word untouched
     ok2, corr2, out2 = code.decode_batch(out[good][:200000])
     assert (ok2 == 1).all() and (corr2 == 0).all() and (out2 == out[good][:200000]).all()
+
+
+@pytest.mark.parametrize("n,t", [(15, 2), (255, 8), (1023, 10), (5000, 12), (8191, 16), (8191, 64), (65535, 16)])
+def test_encode_batch_vs_reference_encoder(gpu_libs, port, n, t):
+    """device encoder (bch_encode_batch) == bch_encode per item == the oracle's encoder, for full,
+    short and ragged data lengths"""
+    from tests.test_emu_kernels import _encode_cases
+    _, host = gpu_libs
+    _encode_cases(host, port, n, t, np.random.default_rng(n * 7 + t))
+
+
+def test_encode_corrupt_decode_round_trip_on_device_encoder(gpu_libs):
+    """200000 random data words -> bch_encode_batch -> 0..t flipped bits (none at bit 0) ->
+    bch_decode_batch gives back the encoder's codewords with corrected = #flips"""
+    _, host = gpu_libs
+    n, t, B = 8191, 16, 200_000
+    code = host.bch_gen_code(n, 2 * t + 1)
+    k = code.data_bits
+    dw = (k + 63) // 64
+    data = synth.splitmix64(0xE1, B * dw).reshape(B, dw)
+    clean = code.encode_batch(data, k)
+    # every codeword of a linear code has zero syndromes: decoding the clean words changes nothing
+    ok0, corr0, out0 = code.decode_batch(clean[:50000])
+    assert (ok0 == 1).all() and (corr0 == 0).all() and (out0 == clean[:50000]).all()
+    rng = np.random.default_rng(0xE1)
+    words = clean.copy()
+    nerr = rng.integers(0, t + 1, B)
+    for e in range(1, t + 1):
+        rows = np.nonzero(nerr >= e)[0]
+        # distinct positions per word: stratify position e into its own band of the codeword
+        band = (n - 1) // t
+        pos = 1 + (e - 1) * band + rng.integers(0, band, rows.size)
+        words[rows, pos // 64] ^= np.uint64(1) << (pos % 64).astype(np.uint64)
+    ok, corr, out = code.decode_batch(words)
+    assert (ok == 1).all() and (corr == nerr).all() and (out == clean).all()
 
 
 def test_reference_demo_sources_build_and_pass(gpu_libs):
