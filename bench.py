@@ -195,7 +195,7 @@ def run_reference(args, rank):
                          "sample": f"{sample} codewords per step, bch_decode on {cores} threads"},
         "e2e": {"value": value, "unit": "codewords/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(args, sample_note=None):
@@ -306,7 +306,8 @@ def run_ours(args, rank, world, local_rank):
                 "kernel_share_of_step": {k: round(v[0] / ksum, 4) for k, v in prof.items()},
                 "whole_step_frac": (B * CW_BYTES_8191 / (total_ms / args.steps * 1e-3) / 1e9) / peak_gbs,
                 "note": "integer/LOP3-bound bitsliced GF(2^13) arithmetic: the HBM fraction is low by "
-                        "construction, see DESIGN.md and profiles/ for the ALU-pipe utilisation"}
+                        "construction, see DESIGN.md section 4 and profiles/r1h_ncu_summary_decode.txt "
+                        "for the ALU-pipe and shared-memory utilisation"}
 
     # ---- end to end through the drop-in host API (pinned host buffers, copies timed) ---------
     e2e = None
@@ -373,7 +374,7 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
             "parity": parity, "decode_stats": stats, "fft": fft, "extras": extras,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def run_fft(args, rank, world, local_rank, lib, host, peak_gbs, peak_src, barrier, max_over_ranks,
@@ -504,8 +505,27 @@ def run_extras(args, rank, world, local_rank, lib, host, barrier, max_over_ranks
     return out
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """the one JSON line goes to the process's original stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
     args = parse()
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner
+    # under torchrun) are diverted to stderr for the whole run
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
