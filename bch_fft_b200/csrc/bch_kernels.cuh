@@ -571,10 +571,12 @@ k_locate(const uint32_t *__restrict__ F, const uint32_t *__restrict__ counts,
 // [32 positions][M planes][32 lanes] shared-memory buffer (first step reads the forward values,
 // last step feeds the zero test).
 constexpr int kLocUMaxK = 5;
+// root queue entries per CTA (kernel parameter qcap; BCHFFT_LOCU_QUEUE overrides it so that tests can
+// force the drain and overflow paths; the emulator build defaults to a tiny queue for the same reason)
 #ifdef BCHFFT_EMU
-constexpr uint32_t kLocUQueue = 24;     // emulator build: tiny queue, so the tests take the drain and overflow paths
+constexpr uint32_t kLocUQueue = 24;
 #else
-constexpr uint32_t kLocUQueue = 4096;   // root queue entries per CTA
+constexpr uint32_t kLocUQueue = 4096;
 #endif
 
 // F2 index of (group, coefficient i, plane b, lane)
@@ -637,11 +639,12 @@ k_elp_fwd_u(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin, 
 
 // Drain the CTA's root queue: entry -> (codeword, reported position); every thread takes
 // independent entries, so the global atomics overlap.  Called by all threads after a barrier.
-__device__ __forceinline__ void locu_flush(const uint32_t *queue, uint32_t *qn, const uint32_t *__restrict__ glist,
+__device__ __forceinline__ void locu_flush(const uint32_t *queue, uint32_t *qn, uint32_t qcap,
+                                           const uint32_t *__restrict__ glist,
                                            const uint32_t *__restrict__ errloc, uint32_t *__restrict__ count,
                                            uint32_t *__restrict__ positions, uint32_t pos_stride)
 {
-  const uint32_t n = *qn < kLocUQueue ? *qn : kLocUQueue;
+  const uint32_t n = *qn < qcap ? *qn : qcap;
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     const uint32_t e = queue[i];
     const uint32_t where = errloc[e >> 10];
@@ -665,7 +668,7 @@ struct LocU {
   uint32_t *queue, *qn;       // shared root queue of the CTA: (tile position << 10) | codeword of the group
   const uint32_t *glist, *errloc;   // overflow path: the group's codeword list, position table
   uint32_t *count, *positions;
-  uint32_t active, kmask, tile0, lane, pos_stride;
+  uint32_t active, kmask, tile0, lane, pos_stride, qcap;
 
   __device__ __forceinline__ void load(uint32_t (&e)[M], uint32_t p, bool from_f) const
   {
@@ -695,7 +698,7 @@ struct LocU {
       const uint32_t bit = (uint32_t)__ffs((int)roots) - 1u;
       roots &= roots - 1u;
       const uint32_t slot = atomicAdd(qn, 1u);
-      if (slot < kLocUQueue) {
+      if (slot < qcap) {
         queue[slot] = ((tile0 + p) << 10) | (lane << 5) | bit;
       } else {
         // queue full (only with pathological root clustering): record directly
@@ -770,7 +773,7 @@ __global__ void __launch_bounds__(BCHFFT_NT_LOC, BCHFFT_MINB_LOCU)
 k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
            const uint32_t *__restrict__ lists, uint32_t batch, uint32_t kmax, FftTables tab,
            const uint32_t *__restrict__ errloc, uint32_t *__restrict__ count,
-           uint32_t *__restrict__ positions, uint32_t pos_stride)
+           uint32_t *__restrict__ positions, uint32_t pos_stride, uint32_t qcap)
 {
   BCHFFT_DYN_SMEM(uint32_t, Wbuf);
   uint32_t *queue = Wbuf + 32u * M * 32u;
@@ -804,6 +807,7 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
   job.count = count;
   job.positions = positions;
   job.pos_stride = pos_stride;
+  job.qcap = qcap;
   job.active = first >= pop ? 0u : (pop - first >= 32u ? 0xFFFFFFFFu : ((1u << (pop - first)) - 1u));
   const uint32_t nsteps = (K + 1u) >> 1;
   const uint32_t ntiles = (1u << M) >> 5;
@@ -817,7 +821,7 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
       __syncthreads();
       const uint32_t fill = s_qn;
       __syncthreads();   // nobody pushes before everybody has read the fill level
-      if (fill > kLocUQueue / 2u) locu_flush(queue, &s_qn, glist, errloc, count, positions, pos_stride);
+      if (fill > qcap / 2u) locu_flush(queue, &s_qn, qcap, glist, errloc, count, positions, pos_stride);
     }
     // steps: level pairs (d, d-1) as radix-4 blocks, a trailing level 0 as radix-2 pairs.  One
     // rolled loop, so that the kernel holds a single copy of each multiply body (the code of all
@@ -839,7 +843,7 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
     }
   }
   __syncthreads();
-  locu_flush(queue, &s_qn, glist, errloc, count, positions, pos_stride);
+  locu_flush(queue, &s_qn, qcap, glist, errloc, count, positions, pos_stride);
 }
 
 

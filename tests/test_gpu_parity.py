@@ -261,6 +261,29 @@ def test_encode_corrupt_decode_round_trip_on_device_encoder(gpu_libs):
     assert (ok == 1).all() and (corr == nerr).all() and (out == clean).all()
 
 
+def test_root_queue_drain_and_overflow_paths_on_device(gpu_libs):
+    """k_locate_u collects roots in a shared-memory queue; BCHFFT_LOCU_QUEUE=6 forces both the
+    mid-kernel drain and the queue-full direct path on the GPU.  Results must not change."""
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from bch_fft_b200 import api, synth\n"
+        "from oracle.pyoracle import Port\n"
+        "host = api.Host(); P = Port(); n, t, B = 8191, 16, 6000\n"
+        "code = host.bch_gen_code(n, 2 * t + 1); pc = P.code(n, t)\n"
+        "bits = (synth.splitmix64(7, 8 * code.data_bits) & np.uint64(1)).astype(np.uint32).reshape(8, -1)\n"
+        "pool = np.stack([code.encode(b) for b in bits])\n"
+        "words, _ = synth.corrupt_codewords(pool, n, t, B, 7, beyond_fraction=0.05)\n"
+        "ok, corr, out = code.decode_batch(words)\n"
+        "rok, rcorr, rout = pc.decode_batch(words)\n"
+        "assert (ok == rok).all() and (corr == rcorr).all() and (out == rout).all()\n"
+        "print('ok')\n")
+    for q in ("6", "1"):
+        env = dict(os.environ, BCHFFT_LOCU_QUEUE=q)
+        res = subprocess.run([os.sys.executable, "-c", code], env=env, capture_output=True, text=True)
+        assert res.returncode == 0 and "ok" in res.stdout, (q, res.stderr[-2000:])
+
+
 def test_reference_demo_sources_build_and_pass(gpu_libs):
     """the reference's bchdemo source, UNCHANGED, linked against our libraries (drop-in check);
     needs the reference tree, so it only runs where /root/reference exists"""

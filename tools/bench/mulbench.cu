@@ -97,6 +97,30 @@ __device__ __forceinline__ void mad_variant(uint32_t (&acc)[M], const uint32_t (
   bs_reduce<M>(q);
 #pragma unroll
   for (int i = 0; i < M; ++i) acc[i] = q[i];
+#elif MB_VARIANT == 5
+  // warp-uniform constant, predication instead of branches: one predicate per bit of c guards the
+  // M XORs of that bit (one asm block each, so that ptxas keeps them predicated)
+  static_assert(M == 13, "variant 5 is written for M = 13");
+  uint32_t p[2 * M - 1];
+#pragma unroll
+  for (int k = 0; k < 2 * M - 1; ++k) p[k] = (k < M) ? acc[k] : 0u;
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const uint32_t bit = (c >> j) & 1u;
+    asm("{ .reg .pred q; setp.ne.u32 q, %26, 0;\n"
+        "@q xor.b32 %0, %0, %13; @q xor.b32 %1, %1, %14; @q xor.b32 %2, %2, %15; @q xor.b32 %3, %3, %16;\n"
+        "@q xor.b32 %4, %4, %17; @q xor.b32 %5, %5, %18; @q xor.b32 %6, %6, %19; @q xor.b32 %7, %7, %20;\n"
+        "@q xor.b32 %8, %8, %21; @q xor.b32 %9, %9, %22; @q xor.b32 %10, %10, %23; @q xor.b32 %11, %11, %24;\n"
+        "@q xor.b32 %12, %12, %25; }"
+        : "+r"(p[j + 0]), "+r"(p[j + 1]), "+r"(p[j + 2]), "+r"(p[j + 3]), "+r"(p[j + 4]), "+r"(p[j + 5]),
+          "+r"(p[j + 6]), "+r"(p[j + 7]), "+r"(p[j + 8]), "+r"(p[j + 9]), "+r"(p[j + 10]), "+r"(p[j + 11]),
+          "+r"(p[j + 12])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]),
+          "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(bit));
+  }
+  bs_reduce<M>(p);
+#pragma unroll
+  for (int i = 0; i < M; ++i) acc[i] = p[i];
 #endif
 }
 
