@@ -281,10 +281,14 @@ __global__ void k_syn_finish(const uint32_t *__restrict__ acc, const uint32_t *_
 //        shared-memory latency.  dynamic smem = 2 * (2^(M+1) + (4 d + 3) * threads) bytes.
 //   SM = false: coefficient buffers in the zero-initialised global scratch bm: [3][d+1][batch]
 //        (coefficient-major), table-free shift-and-add multiply.
+//        With acc != nullptr (decode pipeline) the kernel also does k_syn_finish's job: it builds
+//        its syndrome column straight from the bitsliced accumulators (S_2j = S_j^2 through the
+//        tables), writes flag[], and the global syndrome array is never touched.
 template <int M, bool SM>
-__global__ void k_bm(const uint32_t *__restrict__ syn, const int32_t *__restrict__ flag, uint32_t d,
+__global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ flag, uint32_t d,
                      uint32_t batch, const uint32_t *__restrict__ gexp, const uint32_t *__restrict__ glog,
-                     uint32_t *__restrict__ bm, uint32_t *__restrict__ elp, uint32_t *__restrict__ Lout)
+                     uint32_t *__restrict__ bm, uint32_t *__restrict__ elp, uint32_t *__restrict__ Lout,
+                     const uint32_t *__restrict__ acc, const uint32_t *__restrict__ parity, uint32_t nodd)
 {
   typedef typename std::conditional<SM, uint16_t, uint32_t>::type coef_t;
   const uint32_t order = (1u << M) - 1u;
@@ -306,9 +310,39 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, const int32_t *__restrict
     C = B + bs;
     coef_t *sc = C + bs;
     for (uint32_t j = 0; j < 3u * (d + 1u); ++j) poly[j * cs] = 0;
-    for (uint32_t j = 0; j < d; ++j) sc[j * cs] = (coef_t)(cw < batch ? syn[(size_t)cw * d + j] : 0u);
     s = sc;
-    __syncthreads();
+    __syncthreads();   // tables complete
+    if (acc) {
+      // syndromes from the bitsliced accumulators [slab][nodd][M] (cf. k_syn_finish)
+      uint32_t any = 0u;
+      if (cw < batch) {
+        const uint32_t slab = cw >> 5, l = cw & 31u;
+        uint32_t v = (parity[slab] >> l) & 1u;
+        sc[0] = (coef_t)v;
+        any = v;
+        for (uint32_t i = 1; i < d; ++i) {
+          if (i & 1u) {
+            const uint32_t *a = acc + ((size_t)slab * nodd + (i >> 1)) * M;
+            v = 0u;
+#pragma unroll
+            for (int b = 0; b < M; ++b) v |= ((a[b] >> l) & 1u) << b;
+          } else {
+            const uint32_t h = sc[(i >> 1) * cs];
+            v = 0u;
+            if (h) {
+              uint32_t lg = 2u * (uint32_t)slog[h];
+              if (lg >= order) lg -= order;
+              v = sexp[lg];
+            }
+          }
+          sc[i * cs] = (coef_t)v;
+          any |= v;
+        }
+        flag[cw] = any ? 1 : 0;
+      }
+    } else {
+      for (uint32_t j = 0; j < d; ++j) sc[j * cs] = (coef_t)(cw < batch ? syn[(size_t)cw * d + j] : 0u);
+    }
   } else {
     A = (coef_t *)bm + cw;
     B = A + bs;

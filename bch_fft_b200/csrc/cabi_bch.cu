@@ -121,7 +121,7 @@ static const int kNtSyn = BCHFFT_NT_SYN, kNtLoc = BCHFFT_NT_LOC;
 
 template <int M>
 static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, const Scratch &s,
-                           cudaStream_t st)
+                           cudaStream_t st, bool finish = true)
 {
   const unsigned ns = (unsigned)((cnt + 31) / 32);
   const char *penv = getenv("BCHFFT_SYN_P");
@@ -132,8 +132,9 @@ static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, 
                c->length, (uint32_t)cnt, c->nodd, (const uint32_t *)c->d_lcs, (const uint32_t *)c->d_jinv,
                (const uint32_t *)c->d_start, (const uint32_t *)c->d_foldp, (const uint32_t *)c->d_vbits,
                s.acc, s.parity);
-    BCHFFT_RUN(k_syn_finish<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
-               (const uint32_t *)s.acc, (const uint32_t *)s.parity, c->nodd, c->d, (uint32_t)cnt, s.syn, s.flag);
+    if (finish)
+      BCHFFT_RUN(k_syn_finish<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
+                 (const uint32_t *)s.acc, (const uint32_t *)s.parity, c->nodd, c->d, (uint32_t)cnt, s.syn, s.flag);
     return BCHFFT_OK;
   }
   const size_t smem = sizeof(uint32_t) * ((size_t)c->chunk_pos + c->chunk_pos / 32 + (size_t)c->nodd * M);
@@ -142,16 +143,17 @@ static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, 
                 (const uint32_t *)d_words, c->wpc * 2u, c->length, (uint32_t)cnt, c->chunk_pos,
                 c->nodd, (const uint32_t *)c->d_taps, (const uint32_t *)c->d_fold, c->nsub_total,
                 (const uint32_t *)c->d_vbits, s.acc, s.parity);
-  BCHFFT_RUN(k_syn_finish<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
-                (const uint32_t *)s.acc, (const uint32_t *)s.parity, c->nodd, c->d, (uint32_t)cnt,
-                s.syn, s.flag);
+  if (finish)
+    BCHFFT_RUN(k_syn_finish<M>, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
+                  (const uint32_t *)s.acc, (const uint32_t *)s.parity, c->nodd, c->d, (uint32_t)cnt,
+                  s.syn, s.flag);
   return BCHFFT_OK;
 }
 
+// true when launch_bm takes the shared-memory kernel, which can also finish the syndromes itself
 template <int M>
-static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t st)
+static bool bm_in_smem(const bchfft_code *c, unsigned *nt_out, size_t *smem_out)
 {
-  // shared-memory variant when the tables and the per-thread columns fit next to each other twice per SM
 #ifdef BCHFFT_EMU
   const unsigned nt = 32;
 #else
@@ -159,16 +161,34 @@ static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t 
 #endif
   const size_t smem = sizeof(uint16_t) * (((size_t)2 << M) + (size_t)(4 * c->d + 3) * nt);
   const char *benv = getenv("BCHFFT_BM_SM");
-  if (M <= 14 && smem <= (size_t)110 * 1024 && !(benv && atoi(benv) == 0)) {
+  *nt_out = nt;
+  *smem_out = smem;
+  return M <= 14 && smem <= (size_t)110 * 1024 && !(benv && atoi(benv) == 0);
+}
+
+// fused: the syndromes are still bitsliced accumulators (launch_syndrome(..., finish = false));
+// only valid when bm_in_smem()
+template <int M>
+static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t st, bool fused = false)
+{
+  unsigned nt;
+  size_t smem;
+  if (bm_in_smem<M>(c, &nt, &smem)) {
     constexpr bool kSm = M <= 14;
     BCHFFT_ENSURE_SMEM((k_bm<M, kSm>), c->f->device, smem);
     BCHFFT_RUN((k_bm<M, kSm>), dim3((unsigned)((cnt + nt - 1) / nt)), dim3(nt), smem, st,
-               (const uint32_t *)s.syn, (const int32_t *)s.flag, c->d, (uint32_t)cnt,
-               (const uint32_t *)c->f->d_exp, (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L);
+               (const uint32_t *)s.syn, s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
+               (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L,
+               fused ? (const uint32_t *)s.acc : (const uint32_t *)nullptr, (const uint32_t *)s.parity, c->nodd);
   } else {
+    if (fused) {
+      set_error("bch decode: internal error (fused Berlekamp-Massey without the shared-memory kernel)");
+      return BCHFFT_ERR_ARG;
+    }
     BCHFFT_RUN((k_bm<M, false>), dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
-               (const uint32_t *)s.syn, (const int32_t *)s.flag, c->d, (uint32_t)cnt,
-               (const uint32_t *)c->f->d_exp, (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L);
+               (const uint32_t *)s.syn, s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
+               (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L, (const uint32_t *)nullptr,
+               (const uint32_t *)nullptr, 0u);
   }
   return BCHFFT_OK;
 }
@@ -289,8 +309,13 @@ static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words
     carve(c, w.scratch.p, cnt, pos_stride, M, s);
     BCHFFT_CUDA_TRY(cudaMemsetAsync(w.scratch.p, 0, zero_bytes(c, cnt, M), st));
     uint64_t *wp = d_words + i0 * c->wpc;
-    if ((rc = launch_syndrome<M>(c, wp, cnt, s, st))) return rc;
-    if ((rc = launch_bm<M>(c, cnt, s, st))) return rc;
+    // the shared-memory Berlekamp-Massey kernel un-bitslices the syndromes itself
+    unsigned nt_bm;
+    size_t smem_bm;
+    const char *fenv = getenv("BCHFFT_BM_FUSED");
+    const bool fused = bm_in_smem<M>(c, &nt_bm, &smem_bm) && !(fenv && atoi(fenv) == 0);
+    if ((rc = launch_syndrome<M>(c, wp, cnt, s, st, !fused))) return rc;
+    if ((rc = launch_bm<M>(c, cnt, s, st, fused))) return rc;
     if ((rc = launch_locate<M>(c, w, cnt, s, c->t, st))) return rc;
     BCHFFT_RUN(k_correct, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, wp, c->wpc,
                   (uint32_t)cnt, (const int32_t *)s.flag, (const uint32_t *)s.L, c->t,
