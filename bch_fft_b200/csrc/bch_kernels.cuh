@@ -1,12 +1,19 @@
 // Batched binary-BCH decode kernels (replace libbch/bch.c:228-562 of the reference run once per
 // codeword).  A slab is 32 codewords; bit l of a plane word belongs to codeword l of the slab.
 //
-//   k_syndrome     packed codewords -> bitsliced odd syndromes S_1, S_3, .. (bch.c:228-326)
-//   k_syn_finish   un-bitslice, S_2j = S_j^2, zero test
-//   k_bm           Berlekamp-Massey, one thread per codeword (bch.c:328-404)
-//   k_locate       error-locator evaluation at every field point through the truncated
-//                  additive FFT, root compaction (bch.c:406-490)
+//   k_syndrome_p   packed codewords -> bitsliced odd syndromes S_1, S_3, .. (bch.c:228-326) through
+//                  the universal field-polynomial LFSR on permuted positions (all j coprime to the order)
+//   k_syndrome     same result, general path: one masked LFSR per class
+//   k_syn_finish   un-bitslice, S_2j = S_j^2, zero test (stage-level API; the decode pipeline lets
+//                  k_bm do it)
+//   k_bm           Berlekamp-Massey, one thread per codeword (bch.c:328-404), shared-memory resident
+//                  for small fields
+//   k_bucket / k_elp_fwd[_u]   sort by locator degree, forward phase of the truncated FFT
+//   k_locate_u     error-locator evaluation at every field point, K <= 5 levels, warp lanes = slabs,
+//                  warp-uniform multipliers (bch.c:406-490)
+//   k_locate       same result, general path (tile engine, lanes = positions)
 //   k_correct      ok / corrected bookkeeping and the bit flips (bch.c:531-561)
+//   k_encode       systematic encoder (bch.c:492-506)
 #pragma once
 #include <type_traits>
 #include "bs_common.cuh"
