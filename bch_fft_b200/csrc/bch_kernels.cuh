@@ -139,7 +139,6 @@ k_syndrome(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32
 // The host picks, per class, the chunk length lc and the conjugate j' = j 2^i to work with
 // (S_j = S_j'^(2^(M-i)); the Frobenius power is GF(2)-linear, so it is folded into the fold
 // constants at no cost) that minimise the simulated number of shared-memory wavefronts.
-// grid = slabs; dynamic smem = (ceil(order / 32) * 33 + nodd * M) words.
 template <int M>
 __device__ __forceinline__ void lfsr_field_step(uint32_t (&s)[M], uint32_t in)
 {
@@ -150,6 +149,9 @@ __device__ __forceinline__ void lfsr_field_step(uint32_t (&s)[M], uint32_t in)
   s[0] = in ^ fb;   // bit 0 of the field polynomial is always set
 }
 
+// A CTA takes TWO slabs: their plane words are interleaved (uint2 per position), so that one
+// index update and one 64-bit shared load feed two LFSRs.  grid = ceil(slabs / 2); dynamic smem =
+// 2 * (ceil(order / 32) * 33 + nodd * M) words.
 template <int M>
 __global__ void __launch_bounds__(BCHFFT_NT_SYN, BCHFFT_MINB_SYNP)
 k_syndrome_p(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32_t length_bits,
@@ -159,18 +161,20 @@ k_syndrome_p(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint
 {
   BCHFFT_DYN_SMEM(uint32_t, smem);
   constexpr uint32_t order = (1u << M) - 1u;
-  const uint32_t slab = blockIdx.x;
+  const uint32_t slab0 = blockIdx.x * 2u;
+  const uint32_t nslabs = (batch + 31u) >> 5;
   const uint32_t ngrp = (order + 31u) / 32u;          // 32-position groups of the codeword
-  uint32_t *planes = smem;
-  uint32_t *sacc = smem + ngrp * 33u;                  // [nodd][M]
-  __shared__ uint32_t s_par;
-  if (threadIdx.x == 0) s_par = 0u;
-  for (uint32_t i = threadIdx.x; i < nodd * M; i += blockDim.x) sacc[i] = 0u;
+  uint2 *planes = reinterpret_cast<uint2 *>(smem);
+  uint32_t *sacc = smem + 2u * ngrp * 33u;             // [2][nodd][M]
+  __shared__ uint32_t s_par[2];
+  if (threadIdx.x < 2) s_par[threadIdx.x] = 0u;
+  for (uint32_t i = threadIdx.x; i < 2u * nodd * M; i += blockDim.x) sacc[i] = 0u;
   __syncthreads();
 
-  // phase A: transpose 32 codewords x 32 positions blocks into plane words
-  uint32_t par = 0u;
-  for (uint32_t g = threadIdx.x; g < ngrp; g += blockDim.x) {
+  // phase A: transpose 32 codewords x 32 positions blocks into plane words (both slabs)
+  for (uint32_t w = threadIdx.x; w < 2u * ngrp; w += blockDim.x) {
+    const uint32_t which = w >= ngrp ? 1u : 0u, g = w - which * ngrp;
+    const uint32_t slab = slab0 + which;
     uint32_t x[32];
 #pragma unroll
     for (int l = 0; l < 32; ++l) {
@@ -186,13 +190,15 @@ k_syndrome_p(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint
     }
     transpose32(x);
     const uint32_t vw = (g < words32_per_cw) ? vbits[g] : 0u;
+    uint32_t par = 0u;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(planes + g * 33u) + which;
 #pragma unroll
     for (int b = 0; b < 32; ++b) {
-      planes[g * 33u + b] = x[b];
+      dst[2 * b] = x[b];
       par ^= x[b] & (0u - ((vw >> b) & 1u));
     }
+    if (par) atomicXor(&s_par[which], par);
   }
-  if (par) atomicXor(&s_par, par);
   __syncthreads();
 
   // phase B
@@ -203,43 +209,56 @@ k_syndrome_p(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint
     const uint32_t nsteps = e1 > e0 ? e1 - e0 : 0u;
     const uint32_t step = jinv[ji];
     uint32_t idx = start_idx[item];        // p(e1 - 1)
-    uint32_t s[M];
+    uint32_t s0[M], s1[M];
 #pragma unroll
-    for (int b = 0; b < M; ++b) s[b] = 0u;
+    for (int b = 0; b < M; ++b) s0[b] = s1[b] = 0u;
     // descending e: s <- s X + c_(p(e));  p(e - 1) = p(e) - j^-1 mod order
     // (all chunks of a class but the last have the same length, so the trip counts are warp-uniform)
     const uint32_t main_steps = nsteps & ~7u, pro = nsteps - main_steps;
     for (uint32_t k = 0; k < pro; ++k) {
-      lfsr_field_step<M>(s, planes[idx + (idx >> 5)]);
+      const uint2 in = planes[idx + (idx >> 5)];
+      lfsr_field_step<M>(s0, in.x);
+      lfsr_field_step<M>(s1, in.y);
       const uint32_t t = idx - step, t2 = t + order;
       idx = t < t2 ? t : t2;   // unsigned min: t wrapped around 2^32 exactly when idx < step
     }
     for (uint32_t k = 0; k < main_steps; k += 8u) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        lfsr_field_step<M>(s, planes[idx + (idx >> 5)]);
+        const uint2 in = planes[idx + (idx >> 5)];
+        lfsr_field_step<M>(s0, in.x);
+        lfsr_field_step<M>(s1, in.y);
         const uint32_t t = idx - step, t2 = t + order;
         idx = t < t2 ? t : t2;
       }
     }
     // shift by x^(q lc): out = sum_b s[b] * x^(q lc + b)
     const uint32_t *fc = foldp + (size_t)item * M;
-    uint32_t out[M];
+    uint32_t o0[M], o1[M];
 #pragma unroll
-    for (int k = 0; k < M; ++k) out[k] = 0u;
+    for (int k = 0; k < M; ++k) o0[k] = o1[k] = 0u;
 #pragma unroll
     for (int b = 0; b < M; ++b) {
       const uint32_t c = fc[b];
 #pragma unroll
-      for (int k = 0; k < M; ++k) out[k] ^= s[b] & (0u - ((c >> k) & 1u));
+      for (int k = 0; k < M; ++k) {
+        const uint32_t mask = 0u - ((c >> k) & 1u);
+        o0[k] ^= s0[b] & mask;
+        o1[k] ^= s1[b] & mask;
+      }
     }
 #pragma unroll
-    for (int k = 0; k < M; ++k)
-      if (out[k]) atomicXor(&sacc[ji * M + k], out[k]);
+    for (int k = 0; k < M; ++k) {
+      if (o0[k]) atomicXor(&sacc[ji * M + k], o0[k]);
+      if (o1[k]) atomicXor(&sacc[(nodd + ji) * M + k], o1[k]);
+    }
   }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < nodd * M; i += blockDim.x) acc[(size_t)slab * nodd * M + i] = sacc[i];
-  if (threadIdx.x == 0) parity[slab] = s_par;
+  for (uint32_t i = threadIdx.x; i < 2u * nodd * M; i += blockDim.x) {
+    const uint32_t which = i >= nodd * M ? 1u : 0u;
+    if (slab0 + which < nslabs) acc[(size_t)(slab0 + which) * nodd * M + (i - which * nodd * M)] = sacc[i];
+  }
+  if (threadIdx.x < 2 && slab0 + threadIdx.x < nslabs) parity[slab0 + threadIdx.x] = s_par[threadIdx.x];
 }
 
 // One thread per codeword: syndromes[cw][0..d-1] (u32), flag[cw] (bch.c:317-324).

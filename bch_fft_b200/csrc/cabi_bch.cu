@@ -126,9 +126,9 @@ static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, 
   const unsigned ns = (unsigned)((cnt + 31) / 32);
   const char *penv = getenv("BCHFFT_SYN_P");
   if (c->syn_p && !(penv && atoi(penv) == 0)) {
-    const size_t smem_p = sizeof(uint32_t) * ((size_t)((c->f->order + 31u) / 32u) * 33u + (size_t)c->nodd * M);
+    const size_t smem_p = 2u * sizeof(uint32_t) * ((size_t)((c->f->order + 31u) / 32u) * 33u + (size_t)c->nodd * M);
     BCHFFT_ENSURE_SMEM(k_syndrome_p<M>, c->f->device, smem_p);
-    BCHFFT_RUN(k_syndrome_p<M>, dim3(ns), dim3(kNtSyn), smem_p, st, (const uint32_t *)d_words, c->wpc * 2u,
+    BCHFFT_RUN(k_syndrome_p<M>, dim3((ns + 1u) / 2u), dim3(kNtSyn), smem_p, st, (const uint32_t *)d_words, c->wpc * 2u,
                c->length, (uint32_t)cnt, c->nodd, (const uint32_t *)c->d_lcs, (const uint32_t *)c->d_jinv,
                (const uint32_t *)c->d_start, (const uint32_t *)c->d_foldp, (const uint32_t *)c->d_vbits,
                s.acc, s.parity);
@@ -456,7 +456,7 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
     auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t r = a % b; a = b; b = r; } return a; };
     bool ok = M >= 9 && M <= 15 && length <= order;
     for (uint32_t ji = 0; ji < c->nodd && ok; ji++) ok = gcd((2u * ji + 1u) % order, order) == 1u;
-    const size_t smem_p = sizeof(uint32_t) * ((size_t)((order + 31u) / 32u) * 33u + (size_t)c->nodd * M);
+    const size_t smem_p = 2u * sizeof(uint32_t) * ((size_t)((order + 31u) / 32u) * 33u + (size_t)c->nodd * M);
     if (ok && smem_p <= (size_t)200 * 1024) {
       const uint32_t lc_min = (order + 31u) / 32u, lc_max = lc_min + lc_min / 8u;
       auto inverse = [&](uint32_t v) -> uint32_t {   // v^-1 mod order by the extended Euclid
@@ -477,18 +477,23 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
         const uint32_t step4 = (uint32_t)(((uint64_t)inv * 4u) % order);
         uint64_t total = 0;
         for (uint32_t k = 0; k < longest; k += 4u) {
-          uint8_t load[32] = {0};
-          uint32_t worst = 1;
-          for (uint32_t q = 0; q < 32u; q++) {
-            if (k >= n[q]) continue;
-            const uint32_t bank = (idx[q] + (idx[q] >> 5)) & 31u;
-            if (++load[bank] > worst) worst = load[bank];
-            idx[q] = idx[q] >= step4 ? idx[q] - step4 : idx[q] + order - step4;
+          // 64-bit loads (two slabs per position): each half-warp is one request over 16 bank pairs
+          for (uint32_t half = 0; half < 2u; half++) {
+            uint8_t load[16] = {0};
+            uint32_t worst = 0;
+            for (uint32_t q = half * 16u; q < half * 16u + 16u; q++) {
+              if (k >= n[q]) continue;
+              const uint32_t bank = (idx[q] + (idx[q] >> 5)) & 15u;
+              if (++load[bank] > worst) worst = load[bank];
+              idx[q] = idx[q] >= step4 ? idx[q] - step4 : idx[q] + order - step4;
+            }
+            total += worst;
           }
-          total += worst;
         }
         return total;
       };
+      const char *awenv = getenv("BCHFFT_SYN_ALUW");
+      const uint32_t alu_weight = awenv ? (uint32_t)atoi(awenv) : 4u;   // issue cost of a step in wavefront units (measured best)
       std::vector<uint32_t> jinv(c->nodd), lcs(c->nodd), start((size_t)c->nodd * 32u), foldp((size_t)c->nodd * 32u * M);
       for (uint32_t ji = 0; ji < c->nodd; ji++) {
         const uint32_t j = (2u * ji + 1u) % order;
@@ -498,8 +503,10 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
         for (uint32_t i = 0; i < M; i++, jc = (uint32_t)(((uint64_t)jc * 2u) % order)) {
           const uint32_t inv = inverse(jc);
           for (uint32_t lc = lc_min; lc <= lc_max; lc++) {
-            // idle lanes (chunks beyond the end) are lost throughput: charge them like wavefronts
-            const uint64_t cst = cost(inv, lc) * 32u * lc / order;
+            // time per chunk ~ steps x (issue cost of a step + wavefronts of its load): longer
+            // chunks (idle lanes at the end of the range) cost issue slots even when they remove
+            // conflicts.  cost() sums the wavefronts over every 4th step.
+            const uint64_t cst = cost(inv, lc) + (uint64_t)alu_weight * ((lc + 3u) / 4u);
             if (cst < best) { best = cst; best_i = i; best_lc = lc; best_inv = inv; }
           }
           if (i > 0 && jc == j) break;   // short orbit
