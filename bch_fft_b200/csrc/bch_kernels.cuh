@@ -310,38 +310,67 @@ __global__ void k_syn_finish(const uint32_t *__restrict__ acc, const uint32_t *_
 //        With acc != nullptr (decode pipeline) the kernel also does k_syn_finish's job: it builds
 //        its syndrome column straight from the bitsliced accumulators (S_2j = S_j^2 through the
 //        tables), writes flag[], and the global syndrome array is never touched.
-template <int M, bool SM>
+// LPC = lanes per codeword (SM only; 2 on the GPU): the two lanes of a pair split the coefficient
+// index by parity -- half the sequential work per codeword, and half the shared memory per thread,
+// so three CTAs are resident instead of two.  Rows are padded by 16 entries so that rows j and j+1
+// of one warp's codewords fall on disjoint banks.
+template <int M, bool SM, int LPC>
 __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ flag, uint32_t d,
                      uint32_t batch, const uint32_t *__restrict__ gexp, const uint32_t *__restrict__ glog,
                      uint32_t *__restrict__ bm, uint32_t *__restrict__ elp, uint32_t *__restrict__ Lout,
                      const uint32_t *__restrict__ acc, const uint32_t *__restrict__ parity, uint32_t nodd)
 {
+  static_assert(LPC == 1 || (LPC == 2 && SM), "lane pairs need the shared-memory variant");
   typedef typename std::conditional<SM, uint16_t, uint32_t>::type coef_t;
   const uint32_t order = (1u << M) - 1u;
   BCHFFT_DYN_SMEM(uint16_t, tabs);
   uint16_t *slog = tabs, *sexp = tabs + (1u << M);
-  const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t cs = SM ? (size_t)blockDim.x : (size_t)batch;   // stride between coefficients
-  const size_t bs = (size_t)(d + 1) * cs;                       // stride between buffers
+  const uint32_t per_cta = blockDim.x / LPC;
+  const uint32_t cwl = threadIdx.x / LPC, sub = threadIdx.x % LPC;
+  const uint32_t cw = blockIdx.x * per_cta + cwl;
+  const uint32_t pairmask = LPC == 2 ? (3u << (threadIdx.x & 30u)) : 0u;
+  auto pair_sync = [&]() {
+#ifndef BCHFFT_EMU
+    if (LPC == 2) __syncwarp(pairmask);
+#endif
+  };
+  auto pair_xor = [&](uint32_t v) -> uint32_t {
+#ifndef BCHFFT_EMU
+    if (LPC == 2) v ^= __shfl_xor_sync(pairmask, v, 1);
+#endif
+    return v;
+  };
+  auto pair_max = [&](int v) -> int {
+#ifndef BCHFFT_EMU
+    if (LPC == 2) {
+      const int o = __shfl_xor_sync(pairmask, v, 1);
+      v = o > v ? o : v;
+    }
+#endif
+    return v;
+  };
+  const size_t cs = SM ? (size_t)(per_cta + (LPC == 2 ? 16u : 0u)) : (size_t)batch;   // stride between coefficients
+  const size_t bs = (size_t)(d + 1) * cs;                                              // stride between buffers
   coef_t *A, *B, *C;
   const coef_t *s;
+  uint32_t flagged = 0u;
   if (SM) {
     for (uint32_t i = threadIdx.x; i <= order; i += blockDim.x) {
       slog[i] = (uint16_t)glog[i];
       sexp[i] = (uint16_t)gexp[i];
     }
-    coef_t *poly = (coef_t *)(tabs + (2u << M)) + threadIdx.x;
+    coef_t *poly = (coef_t *)(tabs + (2u << M)) + cwl;
     A = poly;
     B = A + bs;
     C = B + bs;
     coef_t *sc = C + bs;
-    for (uint32_t j = 0; j < 3u * (d + 1u); ++j) poly[j * cs] = 0;
+    for (uint32_t j = sub; j < 3u * (d + 1u); j += LPC) poly[j * cs] = 0;
     s = sc;
     __syncthreads();   // tables complete
     if (acc) {
-      // syndromes from the bitsliced accumulators [slab][nodd][M] (cf. k_syn_finish)
+      // syndromes from the bitsliced accumulators [slab][nodd][M] (cf. k_syn_finish): first lane
       uint32_t any = 0u;
-      if (cw < batch) {
+      if (cw < batch && sub == 0u) {
         const uint32_t slab = cw >> 5, l = cw & 31u;
         uint32_t v = (parity[slab] >> l) & 1u;
         sc[0] = (coef_t)v;
@@ -366,14 +395,18 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
         }
         flag[cw] = any ? 1 : 0;
       }
+      flagged = pair_xor(any ? 1u : 0u);     // the other lane contributes 0
     } else {
-      for (uint32_t j = 0; j < d; ++j) sc[j * cs] = (coef_t)(cw < batch ? syn[(size_t)cw * d + j] : 0u);
+      for (uint32_t j = sub; j < d; j += LPC) sc[j * cs] = (coef_t)(cw < batch ? syn[(size_t)cw * d + j] : 0u);
+      flagged = cw < batch ? (uint32_t)flag[cw] : 0u;
     }
+    pair_sync();
   } else {
     A = (coef_t *)bm + cw;
     B = A + bs;
     C = B + bs;
     s = (const coef_t *)syn + (size_t)cw * d;
+    flagged = cw < batch ? (uint32_t)flag[cw] : 0u;
   }
   const size_t ss = SM ? cs : 1;   // stride between syndromes
   auto mul = [&](uint32_t a, uint32_t b) -> uint32_t {
@@ -393,13 +426,30 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
   };
   if (cw >= batch) return;
   uint32_t L = 0;
-  if (flag[cw]) {
+  if (flagged) {
     uint32_t degA = 0, degB = 0, degC = 0, gap = 1, inv_b_log = 0;
-    B[0] = 1u;
-    C[0] = 1u;
+    if (sub == 0u) {
+      B[0] = 1u;
+      C[0] = 1u;
+    }
+    pair_sync();
     for (uint32_t i = 0; i + 1 < d; ++i) {
-      uint32_t disc = s[(i + 1) * ss];
-      for (uint32_t j = 1; j <= degC; ++j) disc ^= mul(C[j * cs], s[(i + 1 - j) * ss]);
+      // four terms in flight: the loads of a batch are issued before the first table lookup, so the
+      // dependent shared-memory latencies (coefficient -> log -> exp) overlap instead of adding up
+      uint32_t disc = sub == 0u ? (uint32_t)s[(i + 1) * ss] : 0u;
+      for (uint32_t j0 = 1u + sub; j0 <= degC; j0 += 4u * LPC) {
+        uint32_t cv[4], sv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t j = j0 + (uint32_t)u * LPC;
+          const bool in = j <= degC;
+          cv[u] = in ? (uint32_t)C[j * cs] : 0u;
+          sv[u] = in ? (uint32_t)s[(i + 1 - j) * ss] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) disc ^= mul(cv[u], sv[u]);
+      }
+      disc = pair_xor(disc);
       if (!disc) {
         gap++;
         continue;
@@ -409,21 +459,31 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
       if (sl >= order) sl -= order;
       const uint32_t scale = SM ? (uint32_t)sexp[sl] : gexp[sl];
       const uint32_t hiB = degB + gap;
-      const uint32_t keep = gap < degC + 1 ? gap : degC + 1;
-      uint32_t j = 0;
-      for (; j < keep; ++j) A[j * cs] = C[j * cs];
-      for (; j < gap; ++j) A[j * cs] = 0u;
-      for (; j <= hiB; ++j) A[j * cs] = (coef_t)mul_log(B[(j - gap) * cs], sl, scale);
-      for (; j <= degC; ++j) A[j * cs] = 0u;
-      if (degC != hiB) {
-        degA = degC > hiB ? degC : hiB;
-        for (j = gap; j <= degC; ++j) A[j * cs] ^= C[j * cs];
-      } else {
-        for (j = gap; j <= degC; ++j) {
-          const uint32_t v = A[j * cs] ^ C[j * cs];
-          A[j * cs] = (coef_t)v;
-          if (v) degA = j;
+      // A = C below `gap`, scale * B shifted by gap (+ C) from there on -- the reference's four copy
+      // loops and its XOR loop (bch.c:352-385) in one sweep over j, split between the lanes by j
+      const uint32_t top = hiB > degC ? hiB : degC;
+      int last_nz = -1;
+      for (uint32_t j0 = sub; j0 <= top; j0 += 4u * LPC) {
+        uint32_t bv[4], cv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t j = j0 + (uint32_t)u * LPC;
+          bv[u] = (j >= gap && j <= hiB) ? (uint32_t)B[(j - gap) * cs] : 0u;
+          cv[u] = j <= degC ? (uint32_t)C[j * cs] : 0u;
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t j = j0 + (uint32_t)u * LPC;
+          const uint32_t v = mul_log(bv[u], sl, scale) ^ cv[u];
+          if (j >= gap && j <= degC && v) last_nz = (int)j;
+          if (j <= top) A[j * cs] = (coef_t)v;
+        }
+      }
+      if (degC != hiB) {
+        degA = top;
+      } else {
+        last_nz = pair_max(last_nz);
+        if (last_nz >= 0) degA = (uint32_t)last_nz;   // otherwise degA keeps its previous value (bch.c:379-384)
       }
       if (2u * L <= i) {
         L = i + 1u - L;
@@ -436,13 +496,15 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
       }
       { coef_t *t = C; C = A; A = t; }
       degC = degA;
+      pair_sync();   // the partner's half of the new C is visible before the next discrepancy
     }
-  } else {
+  } else if (sub == 0u) {
     C[0] = 1u;
   }
-  Lout[cw] = L;
+  pair_sync();
+  if (sub == 0u) Lout[cw] = L;
   uint32_t *e = elp + (size_t)cw * (d + 1);
-  for (uint32_t j = 0; j <= d; ++j) e[j] = C[j * cs];
+  for (uint32_t j = sub; j <= d; j += LPC) e[j] = C[j * cs];
 }
 
 // ---- root search ----------------------------------------------------------------------------

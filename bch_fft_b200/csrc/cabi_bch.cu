@@ -107,10 +107,12 @@ static size_t scratch_bytes(const bchfft_code *c, size_t cnt, uint32_t pos_strid
                              cnt * (d + 1) + cnt + cnt + cnt * pos_stride) + 64;
 }
 
-static size_t zero_bytes(const bchfft_code *c, size_t cnt, int M)
+// acc, parity, count and (with_bm) the global Berlekamp-Massey buffers; the shared-memory BM kernel
+// does not touch the latter
+static size_t zero_bytes(const bchfft_code *c, size_t cnt, int M, bool with_bm = true)
 {
   const size_t ns = (cnt + 31) / 32, d = c->d;
-  return sizeof(uint32_t) * (ns * c->nodd * M + ns + cnt + 3 * (d + 1) * cnt);
+  return sizeof(uint32_t) * (ns * c->nodd * M + ns + cnt + (with_bm ? 3 * (d + 1) * cnt : 0));
 }
 
 #ifdef BCHFFT_EMU
@@ -150,16 +152,24 @@ static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, 
   return BCHFFT_OK;
 }
 
+#ifdef BCHFFT_EMU
+static const unsigned kBmThreads = 32;
+static constexpr int kBmLpc = 1;      // the emulator has no warp shuffles
+#else
+static const unsigned kBmThreads = 256;
+#ifndef BCHFFT_BM_LPC
+#define BCHFFT_BM_LPC 1   /* measured: lane pairs (2) are slower, 1.12 ms against 1.02 ms */
+#endif
+static constexpr int kBmLpc = BCHFFT_BM_LPC;      // lanes per codeword of the shared-memory kernel
+#endif
+
 // true when launch_bm takes the shared-memory kernel, which can also finish the syndromes itself
 template <int M>
 static bool bm_in_smem(const bchfft_code *c, unsigned *nt_out, size_t *smem_out)
 {
-#ifdef BCHFFT_EMU
-  const unsigned nt = 32;
-#else
-  const unsigned nt = 256;
-#endif
-  const size_t smem = sizeof(uint16_t) * (((size_t)2 << M) + (size_t)(4 * c->d + 3) * nt);
+  const unsigned nt = kBmThreads;
+  const size_t cs = nt / kBmLpc + (kBmLpc == 2 ? 16u : 0u);
+  const size_t smem = sizeof(uint16_t) * (((size_t)2 << M) + (size_t)(4 * c->d + 3) * cs);
   const char *benv = getenv("BCHFFT_BM_SM");
   *nt_out = nt;
   *smem_out = smem;
@@ -175,8 +185,10 @@ static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t 
   size_t smem;
   if (bm_in_smem<M>(c, &nt, &smem)) {
     constexpr bool kSm = M <= 14;
-    BCHFFT_ENSURE_SMEM((k_bm<M, kSm>), c->f->device, smem);
-    BCHFFT_RUN((k_bm<M, kSm>), dim3((unsigned)((cnt + nt - 1) / nt)), dim3(nt), smem, st,
+    constexpr int kLpc = kSm ? kBmLpc : 1;
+    const unsigned per_cta = nt / kLpc;
+    BCHFFT_ENSURE_SMEM((k_bm<M, kSm, kLpc>), c->f->device, smem);
+    BCHFFT_RUN((k_bm<M, kSm, kLpc>), dim3((unsigned)((cnt + per_cta - 1) / per_cta)), dim3(nt), smem, st,
                (const uint32_t *)s.syn, s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
                (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L,
                fused ? (const uint32_t *)s.acc : (const uint32_t *)nullptr, (const uint32_t *)s.parity, c->nodd);
@@ -185,7 +197,7 @@ static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t 
       set_error("bch decode: internal error (fused Berlekamp-Massey without the shared-memory kernel)");
       return BCHFFT_ERR_ARG;
     }
-    BCHFFT_RUN((k_bm<M, false>), dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
+    BCHFFT_RUN((k_bm<M, false, 1>), dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
                (const uint32_t *)s.syn, s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
                (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L, (const uint32_t *)nullptr,
                (const uint32_t *)nullptr, 0u);
@@ -307,13 +319,14 @@ static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words
     const size_t cnt = batch - i0 < chunk ? batch - i0 : chunk;
     Scratch s;
     carve(c, w.scratch.p, cnt, pos_stride, M, s);
-    BCHFFT_CUDA_TRY(cudaMemsetAsync(w.scratch.p, 0, zero_bytes(c, cnt, M), st));
     uint64_t *wp = d_words + i0 * c->wpc;
     // the shared-memory Berlekamp-Massey kernel un-bitslices the syndromes itself
     unsigned nt_bm;
     size_t smem_bm;
     const char *fenv = getenv("BCHFFT_BM_FUSED");
-    const bool fused = bm_in_smem<M>(c, &nt_bm, &smem_bm) && !(fenv && atoi(fenv) == 0);
+    const bool bm_sm = bm_in_smem<M>(c, &nt_bm, &smem_bm);
+    const bool fused = bm_sm && !(fenv && atoi(fenv) == 0);
+    BCHFFT_CUDA_TRY(cudaMemsetAsync(w.scratch.p, 0, zero_bytes(c, cnt, M, !bm_sm), st));
     if ((rc = launch_syndrome<M>(c, wp, cnt, s, st, !fused))) return rc;
     if ((rc = launch_bm<M>(c, cnt, s, st, fused))) return rc;
     if ((rc = launch_locate<M>(c, w, cnt, s, c->t, st))) return rc;
