@@ -318,7 +318,8 @@ template <int M, bool SM, int LPC>
 __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ flag, uint32_t d,
                      uint32_t batch, const uint32_t *__restrict__ gexp, const uint32_t *__restrict__ glog,
                      uint32_t *__restrict__ bm, uint32_t *__restrict__ elp, uint32_t *__restrict__ Lout,
-                     const uint32_t *__restrict__ acc, const uint32_t *__restrict__ parity, uint32_t nodd)
+                     const uint32_t *__restrict__ acc, const uint32_t *__restrict__ parity, uint32_t nodd,
+                     uint32_t elp_limit)
 {
   static_assert(LPC == 1 || (LPC == 2 && SM), "lane pairs need the shared-memory variant");
   typedef typename std::conditional<SM, uint16_t, uint32_t>::type coef_t;
@@ -503,8 +504,12 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
   }
   pair_sync();
   if (sub == 0u) Lout[cw] = L;
+  // elp_limit = d: the whole buffer (stage-level API, bch.c leaves it in m_C_elp); smaller: only what
+  // the root search reads, C[0..L] of the codewords it will look at (L <= elp_limit)
   uint32_t *e = elp + (size_t)cw * (d + 1);
-  for (uint32_t j = sub; j <= d; j += LPC) e[j] = C[j * cs];
+  const uint32_t upto = elp_limit >= d ? d : (L <= elp_limit ? L : 0u);
+  if (elp_limit >= d || (L >= 1u && L <= elp_limit))
+    for (uint32_t j = sub; j <= upto; j += LPC) e[j] = C[j * cs];
 }
 
 // ---- root search ----------------------------------------------------------------------------

@@ -179,7 +179,8 @@ static bool bm_in_smem(const bchfft_code *c, unsigned *nt_out, size_t *smem_out)
 // fused: the syndromes are still bitsliced accumulators (launch_syndrome(..., finish = false));
 // only valid when bm_in_smem()
 template <int M>
-static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t st, bool fused = false)
+static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t st, bool fused = false,
+                     uint32_t elp_limit = 0xFFFFFFFFu)
 {
   unsigned nt;
   size_t smem;
@@ -191,7 +192,8 @@ static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t 
     BCHFFT_RUN((k_bm<M, kSm, kLpc>), dim3((unsigned)((cnt + per_cta - 1) / per_cta)), dim3(nt), smem, st,
                (const uint32_t *)s.syn, s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
                (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L,
-               fused ? (const uint32_t *)s.acc : (const uint32_t *)nullptr, (const uint32_t *)s.parity, c->nodd);
+               fused ? (const uint32_t *)s.acc : (const uint32_t *)nullptr, (const uint32_t *)s.parity, c->nodd,
+               elp_limit);
   } else {
     if (fused) {
       set_error("bch decode: internal error (fused Berlekamp-Massey without the shared-memory kernel)");
@@ -200,7 +202,7 @@ static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t 
     BCHFFT_RUN((k_bm<M, false, 1>), dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
                (const uint32_t *)s.syn, s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
                (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L, (const uint32_t *)nullptr,
-               (const uint32_t *)nullptr, 0u);
+               (const uint32_t *)nullptr, 0u, elp_limit);
   }
   return BCHFFT_OK;
 }
@@ -328,7 +330,7 @@ static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words
     const bool fused = bm_sm && !(fenv && atoi(fenv) == 0);
     BCHFFT_CUDA_TRY(cudaMemsetAsync(w.scratch.p, 0, zero_bytes(c, cnt, M, !bm_sm), st));
     if ((rc = launch_syndrome<M>(c, wp, cnt, s, st, !fused))) return rc;
-    if ((rc = launch_bm<M>(c, cnt, s, st, fused))) return rc;
+    if ((rc = launch_bm<M>(c, cnt, s, st, fused, c->t))) return rc;
     if ((rc = launch_locate<M>(c, w, cnt, s, c->t, st))) return rc;
     BCHFFT_RUN(k_correct, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, wp, c->wpc,
                   (uint32_t)cnt, (const int32_t *)s.flag, (const uint32_t *)s.L, c->t,
