@@ -713,15 +713,19 @@ __device__ __forceinline__ size_t f2_index(uint32_t group, uint32_t kmax, uint32
   return ((((size_t)group << kmax) + i) * M_ + b) * 32u + lane;
 }
 
-// forward phase like k_elp_fwd, output in the group layout.  grid as k_elp_fwd.
+// forward phase like k_elp_fwd, output in the group layout; all buckets in one launch:
+// grid = (ceil(slabs / 8), kmax), bucket K = blockIdx.y + 1 (K <= 5 here), a CTA takes 256
+// coefficient columns = 2^(8-K) slabs; fwd_descs[K] = forward pass of bucket K.
 template <int M>
 __global__ void __launch_bounds__(256)
 k_elp_fwd_u(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin, uint32_t d,
             const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists, uint32_t batch,
-            uint32_t sb, uint32_t kmax, FftTables tab, PassDesc fwd, uint32_t *__restrict__ F2)
+            uint32_t kmax, FftTables tab, const PassDesc *__restrict__ fwd_descs, uint32_t *__restrict__ F2)
 {
   BCHFFT_DYN_SMEM(uint32_t, S);
-  const uint32_t K = fwd.dom_bits, TK = 1u << K, tt = K + sb, T = 1u << tt;
+  const uint32_t K = blockIdx.y + 1u, sb = 8u - K;
+  const PassDesc &fwd = fwd_descs[K];
+  const uint32_t TK = 1u << K, tt = K + sb, T = 1u << tt;
   const uint32_t pop = counts[K], nslabs = (pop + 31u) >> 5;
   const uint32_t slab0 = blockIdx.x << sb;
   if (slab0 >= nslabs) return;

@@ -232,7 +232,8 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
   const bool use_u = kmax <= kLocUMaxK && M >= 5 && M <= 22 && !(uenv && atoi(uenv) == 0);
   const unsigned ngroups = (unsigned)(cnt / 1024) + (unsigned)kmax + 1u;   // >= sum_K ceil(ceil(count_K/32)/32)
   // work buffer: butterfly descriptors, bucket counts, bucket lists, forward values
-  const size_t desc_bytes = (sizeof(PassDesc) * (kMaxBuckets + 1) + 255) & ~(size_t)255;
+  // descriptors: [0, kMaxBuckets] backward (butterfly) passes, [kMaxBuckets + 1, 2 kMaxBuckets + 1] forward passes
+  const size_t desc_bytes = (sizeof(PassDesc) * 2 * (kMaxBuckets + 1) + 255) & ~(size_t)255;
   const size_t f_words = use_u ? (((size_t)ngroups << kmax) * M * 32u) : (((size_t)nvirt << kmax) * PS);
   const size_t need = desc_bytes + ((kMaxBuckets + 1) + (size_t)(kMaxBuckets + 1) * cnt + f_words) * 4 + 256;
   int rc = w.fwd_buf.reserve(need);
@@ -242,11 +243,13 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
   uint32_t *lists = counts + (kMaxBuckets + 1);
   // forward values are read and written as 16-byte vectors
   uint32_t *F = (uint32_t *)(((uintptr_t)(lists + (size_t)(kMaxBuckets + 1) * cnt) + 15) & ~(uintptr_t)15);
-  std::vector<PassDesc> fwd(kmax + 1), bwd(kMaxBuckets + 1);
+  std::vector<PassDesc> fwd(kMaxBuckets + 1), bwd(kMaxBuckets + 1);
   for (int K = 1; K <= kmax; K++) locate_descs(M, K, t, c->f->twist_free, fwd[K], bwd[K]);
   if (w.descs_t != t || w.descs_kmax != kmax || w.descs_at != (void *)d_descs) {
     // the descriptors only depend on (t, kmax): uploaded once per work buffer
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(d_descs, bwd.data(), sizeof(PassDesc) * (kMaxBuckets + 1),
+                                    cudaMemcpyHostToDevice, st));
+    BCHFFT_CUDA_TRY(cudaMemcpyAsync(d_descs + (kMaxBuckets + 1), fwd.data(), sizeof(PassDesc) * (kMaxBuckets + 1),
                                     cudaMemcpyHostToDevice, st));
     BCHFFT_CUDA_TRY(cudaStreamSynchronize(st));          // bwd is a stack object
     w.descs_t = t;
@@ -257,14 +260,15 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
   BCHFFT_RUN(k_bucket, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, (const int32_t *)s.flag,
              (const uint32_t *)s.L, tcap, (uint32_t)cnt, counts, lists);
   if (use_u) {
-    for (int K = 1; K <= kmax; K++) {
-      uint32_t sb = 0;
-      while ((1u << (K + sb)) < 256u) sb++;
-      const size_t smem_f = sizeof(uint32_t) * M * ((size_t)1 << (K + sb));
+    // forward phase of all buckets in one launch (blockIdx.y = K - 1): 256 coefficient columns per CTA,
+    // i.e. 2^(8-K) slabs; CTAs beyond a bucket's population exit
+    {
+      const size_t smem_f = sizeof(uint32_t) * M * 256u;
       BCHFFT_ENSURE_SMEM(k_elp_fwd_u<M>, c->f->device, smem_f);
-      BCHFFT_RUN(k_elp_fwd_u<M>, dim3((ns + (1u << sb) - 1u) >> sb), dim3(256), smem_f, st,
+      BCHFFT_RUN(k_elp_fwd_u<M>, dim3((ns + 7u) >> 3, (unsigned)kmax), dim3(256), smem_f, st,
                  (const uint32_t *)s.elp, (const uint32_t *)s.L, c->d, (const uint32_t *)counts,
-                 (const uint32_t *)lists, (uint32_t)cnt, sb, (uint32_t)kmax, c->f->tab, fwd[K], F);
+                 (const uint32_t *)lists, (uint32_t)cnt, (uint32_t)kmax, c->f->tab,
+                 (const PassDesc *)(d_descs + (kMaxBuckets + 1)), F);
     }
     // enough CTAs per group to fill the machine and to even out the buckets' different costs
     const unsigned ntiles = (1u << M) >> 5;
