@@ -278,7 +278,7 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
     uint32_t qcap = kLocUQueue;
     const char *qenv = getenv("BCHFFT_LOCU_QUEUE");
     if (qenv && atoi(qenv) >= 1 && atoi(qenv) <= (int)kLocUQueue) qcap = (uint32_t)atoi(qenv);
-    const size_t smem_u = sizeof(uint32_t) * (32u * M * 32u + kLocUQueue);
+    const size_t smem_u = sizeof(uint32_t) * (32u * M * 32u + qcap);
     BCHFFT_ENSURE_SMEM(k_locate_u<M>, c->f->device, smem_u);
     BCHFFT_RUN(k_locate_u<M>, dim3(gx, ngroups), dim3(kNtLoc), smem_u, st, (const uint32_t *)F,
                (const uint32_t *)counts, (const uint32_t *)lists, (uint32_t)cnt, (uint32_t)kmax, c->f->tab,
