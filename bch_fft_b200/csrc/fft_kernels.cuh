@@ -305,11 +305,15 @@ __device__ __forceinline__ void tile_store(const uint32_t *S, uint32_t T, uint32
   }
 }
 
-// TW(d): a[p] *= tw[d][p >> d]
-template <int M>
+// TW(d): a[p] *= tw[d][p >> d].  UNI: when the five lowest local bits (the lanes of a warp) all map
+// to global position bits below d, the multiplier is warp-uniform: branch over its set bits.
+template <int M, bool UNI = false>
 __device__ __forceinline__ void tile_twist(uint32_t *S, uint32_t T, const TileGeom &g,
                                            const uint32_t *__restrict__ tw_d, uint32_t d)
 {
+  // highest global bit driven by local bits 0..4
+  const uint32_t top_lane_bit = g.n0 >= 5u ? g.a0 + 4u : g.a1 + (4u - g.n0);
+  const bool uni = UNI && T >= 32u && top_lane_bit < d;
   constexpr int U = 4;   // constants of four positions are fetched before the first multiply
   for (uint32_t base = threadIdx.x; base < T; base += U * blockDim.x) {
     uint32_t c[U];
@@ -325,9 +329,18 @@ __device__ __forceinline__ void tile_twist(uint32_t *S, uint32_t T, const TileGe
       uint32_t a[M];
 #pragma unroll
       for (int b = 0; b < M; ++b) a[b] = S[b * T + sl];
-      bs_mul_scalar<M>(a, c[u]);
+      if (UNI && uni) {
+        uint32_t r[M];
 #pragma unroll
-      for (int b = 0; b < M; ++b) S[b * T + sl] = a[b];
+        for (int b = 0; b < M; ++b) r[b] = 0u;
+        bs_mad_uniform<M>(r, a, c[u]);
+#pragma unroll
+        for (int b = 0; b < M; ++b) S[b * T + sl] = r[b];
+      } else {
+        bs_mul_scalar<M>(a, c[u]);
+#pragma unroll
+        for (int b = 0; b < M; ++b) S[b * T + sl] = a[b];
+      }
     }
   }
 }
@@ -734,7 +747,7 @@ __device__ __forceinline__ void tile_run_ops(uint32_t *S, uint32_t T, uint32_t t
     const PassOp op = desc.ops[i];
     BCHFFT_MARK(100u + op.type * 100u + op.d);
     if (op.type == OP_TW) {
-      tile_twist<M>(S, T, g, tab.tw + tab.tw_off[op.d], op.d);
+      tile_twist<M, UNI>(S, T, g, tab.tw + tab.tw_off[op.d], op.d);
       i += 1;
     } else if (op.type == OP_TY) {
       const uint32_t c = taylor_run(desc, g, i);
