@@ -28,6 +28,11 @@ void additive_DFT_ref(TfiniteField* p_f, uint32_t* p_poly, uint32_t p_poly_degre
 int additive_fft_batch(TfiniteField* p_f, const uint32_t* p_polys, uint32_t* po_results,
                        uint32_t p_num_terms, size_t p_count);
 
+/* host-only diagnostic exported by the reference's libfft (libfft/additive_fft.c:181; not in its
+ * header): 1 when rows P_0 .. P_(m-1) of `div` (m+1 coefficients each, on X^degrees[]) are the
+ * subspace polynomials of span{1, 2, .., 2^(i-1)} */
+int check_fft_polynomials(TfiniteField* p_f, uint32_t* div, uint32_t* degrees, uint32_t* y);
+
 #ifdef __cplusplus
 }
 #endif

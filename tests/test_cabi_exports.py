@@ -39,7 +39,18 @@ def test_host_library_exports_reference_symbols():
                  "multiplicative_FFT", "evaluate_polynomial_multiplicative_FFT",
                  "create_binary_finite_field", "free_finite_field", "multiply", "multiply_by_log",
                  "square", "inverse", "get_bit", "set_bit", "add_bit", "degree_to_packed_size",
-                 "additive_fft_batch", "bch_decode_batch", "bch_encode_batch", "multiplicative_fft_batch"):
+                 "additive_fft_batch", "bch_decode_batch", "bch_encode_batch", "multiplicative_fft_batch",
+                 # host-only symbols the reference's objects export (SURVEY 8b "complete the libs")
+                 "evaluate_sparse_polynomial", "evaluate_sparse_polynomial_ref", "evaluate_sparse_polynomial_log",
+                 "multiply_polynomial_by_monomial", "euclidean_division_sparse_reductor",
+                 "euclidean_division_sparse_reductor_ref", "euclidean_division_packed_inplace_gf2",
+                 "word_size", "wordsize_to_max_degree", "degree_packed", "degree_packed_u32",
+                 "degree_to_packed_size_u32", "degree_to_packed_pos", "degree_to_packed_pos_u32",
+                 "bch_build_polynomial", "bch_explore_cycles", "bch_reduce_syndrome", "bch_find_best_offset",
+                 "numFactors", "factors", "factorOffset", "getFactorSum", "DFT_direct",
+                 "multiplicative_FFT_compute_step", "multiplicative_FFT_reorder_step",
+                 "multiplicative_FFT_step_chaining", "check_fft_polynomials",
+                 "absolute_time", "init_time", "urand", "compare_results"):
         assert hasattr(lib, name), name
 
 

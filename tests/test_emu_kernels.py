@@ -314,3 +314,85 @@ def test_emu_edge_cases_and_errors(emu_libs, port):
         host.bch_gen_code(255, 255)                       # m_packed_gen_poly == NULL
     with pytest.raises(ValueError):
         host.create_binary_finite_field(31)               # exp == log == NULL
+
+
+@pytest.mark.parametrize("m", [8, 9, 12])
+def test_host_only_multiplicative_building_blocks(emu_libs, port, m):
+    """multiplicative_FFT_step_chaining / _compute_step / _reorder_step (host-only symbols the
+    reference's libfft exports, libfft/multiplicative_fft.c:124-257) against the oracle's
+    transform and the naive DFT_direct; the log-form input survives a compute step."""
+    import ctypes as C
+    _, host = emu_libs
+    L = host.lib
+    f = host.create_binary_finite_field(m)
+    n, order = f.n, f.n - 1
+    u32p = C.POINTER(C.c_uint32)
+    L.numFactors.restype = C.c_uint32
+    L.numFactors.argtypes = [C.c_uint32]
+    L.factors.restype = u32p
+    L.factors.argtypes = [C.c_uint32]
+    nf, facts = L.numFactors(m), L.factors(m)
+    rng = np.random.default_rng(900 + m)
+    data = rng.integers(0, n, order, dtype=np.uint32)
+    data[rng.integers(0, order, order // 8)] = 0          # logzero entries take the skip branch
+    want = port.mult_fft(m, data)
+    logs = np.ctypeslib.as_array(f.c.log, (n,))[data].astype(np.uint32)
+    buf = np.zeros(order, np.uint32)
+    fp = C.byref(f.c)
+    as_p = lambda a: a.ctypes.data_as(u32p)
+    # one compute step on its own: input logs unchanged, rows are size-N DFTs
+    before = logs.copy()
+    local = order // facts[0]
+    L.multiplicative_FFT_compute_step(fp, as_p(logs), as_p(buf), C.c_uint32(local), C.c_uint32(1), C.c_uint32(1))
+    assert (logs == before).all()
+    N, count = order // local, local
+    exp = np.ctypeslib.as_array(f.c.exp, (n,))
+    for i, s in ((0, 0), (1, 0), (N - 1, count - 1)):
+        acc = 0
+        for j in range(N):
+            d = int(before[s + count * j])
+            if d != f.c.logzero:
+                acc ^= int(exp[(d + local * i * j) % order])
+        assert int(buf[s + count * i]) == acc
+    # the whole chain
+    L.multiplicative_FFT_step_chaining(fp, as_p(logs), as_p(buf), facts, C.c_uint32(nf), C.c_uint32(order),
+                                       C.c_uint32(1))
+    assert (logs == want).all()
+    if m <= 9:
+        naive = data.copy()
+        L.DFT_direct(fp, as_p(naive), as_p(buf))
+        assert (naive == want).all()
+
+
+@pytest.mark.parametrize("m", [4, 8, 11])
+def test_host_only_check_fft_polynomials(emu_libs, port, m):
+    """check_fft_polynomials (libfft/additive_fft.c:181-262) accepts the subspace polynomials
+    P_i = P_(i-1)^2 + y_(i-1) P_(i-1) and rejects a corrupted table"""
+    import ctypes as C
+    _, host = emu_libs
+    L = host.lib
+    f = host.create_binary_finite_field(m)
+    u32p = C.POINTER(C.c_uint32)
+    L.check_fft_polynomials.restype = C.c_int
+    mul = lambda a, b: int(f.multiply(a, b))
+    div = np.zeros((m, m + 1), np.uint32)
+    div[0, 1] = 1                                          # P_0 = X
+    for i in range(1, m):
+        prev = div[i - 1]
+        y = 0                                              # P_(i-1)(2^(i-1))
+        for j in range(i + 1):
+            v = 1 << (i - 1)
+            for _ in range(j - 1):
+                v = mul(v, v)
+            if j >= 1:
+                y ^= mul(int(prev[j]), v)
+        for j in range(1, i + 2):
+            sq = mul(int(prev[j - 1]), int(prev[j - 1])) if j >= 2 else 0
+            div[i, j] = sq ^ mul(y, int(prev[j]))
+    degrees = np.array([0] + [1 << j for j in range(m + 1)], np.uint32)
+    yv = np.zeros(m, np.uint32)
+    args = lambda d: (C.byref(f.c), d.ctypes.data_as(u32p), degrees.ctypes.data_as(u32p), yv.ctypes.data_as(u32p))
+    assert L.check_fft_polynomials(*args(div)) == 1
+    bad = div.copy()
+    bad[m - 1, 1] ^= 1
+    assert L.check_fft_polynomials(*args(bad)) == 0
