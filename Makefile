@@ -1,6 +1,7 @@
 # Top-level build.
 #   make            CUDA C-ABI library (nvcc, sm_100a) + host C libraries + oracle checkers
 #   make emu        CPU-emulator builds used by the CPU-only unit tests (test infrastructure)
+#   make stream     host/bchstream: streaming decoder CLI on the drop-in library
 #   make demos      build the reference's own fftdemo/bchdemo sources UNCHANGED against our
 #                   libraries (needs /root/reference; drop-in check)
 ROOT := $(dir $(abspath $(lastword $(MAKEFILE_LIST))))
@@ -10,7 +11,7 @@ HOSTC := $(ROOT)host/base.c $(ROOT)host/context.c $(ROOT)host/fft.c $(ROOT)host/
 HFLAGS := -std=gnu99 -O2 -fPIC -Wall -Wextra -I$(ROOT)include -I$(ROOT)host
 REF  ?= /root/reference
 
-all: cuda host oracle
+all: cuda host oracle stream
 cuda:
 	$(MAKE) -C $(CSRC) all
 emu: oracle
@@ -41,8 +42,17 @@ demos-emu: emu
 	    -L$(ROOT)host -lbchfft_host_emu -Wl,-rpath,$(ROOT)host -lm
 	$(CC) -std=gnu99 -O2 -I$(ROOT)include -o $(ROOT)host/bchdemo_emu $(REF)/bch/main.c \
 	    -L$(ROOT)host -lbchfft_host_emu -Wl,-rpath,$(ROOT)host -lm
+# streaming decoder CLI: packed codewords stdin -> stdout through bch_decode_batch
+stream: host
+	$(CC) -std=gnu99 -O2 -Wall -Wextra -I$(ROOT)include -o $(ROOT)host/bchstream $(ROOT)host/bchstream.c \
+	    -L$(ROOT)host -lbchfft_host -L$(CSRC) -lbchfft_cuda -Wl,-rpath,'$$ORIGIN' \
+	    -Wl,-rpath,'$$ORIGIN/../bch_fft_b200/csrc' -lpthread -lm
+stream-emu: emu
+	$(CC) -std=gnu99 -O2 -Wall -Wextra -I$(ROOT)include -o $(ROOT)host/bchstream_emu $(ROOT)host/bchstream.c \
+	    -L$(ROOT)host -lbchfft_host_emu -L$(CSRC) -lbchfft_emu -Wl,-rpath,'$$ORIGIN' \
+	    -Wl,-rpath,'$$ORIGIN/../bch_fft_b200/csrc' -lpthread -lm
 clean:
 	$(MAKE) -C $(CSRC) clean
 	$(MAKE) -C $(ROOT)oracle clean
 	rm -rf $(ROOT)host/build $(ROOT)host/*.so $(ROOT)host/*.a $(ROOT)host/*demo*
-.PHONY: all cuda emu host oracle demos demos-emu clean
+.PHONY: all cuda emu host oracle demos demos-emu stream stream-emu clean

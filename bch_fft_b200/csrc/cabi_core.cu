@@ -181,6 +181,22 @@ extern "C" int bchfft_dev_free(int device, void *p)
   return BCHFFT_OK;
 }
 
+extern "C" int bchfft_pinned_alloc(size_t bytes, void **out)
+{
+  if (!out) {
+    set_error("bchfft_pinned_alloc: null argument");
+    return BCHFFT_ERR_ARG;
+  }
+  BCHFFT_CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1));
+  return BCHFFT_OK;
+}
+
+extern "C" int bchfft_pinned_free(void *p)
+{
+  BCHFFT_CUDA_TRY(cudaFreeHost(p));
+  return BCHFFT_OK;
+}
+
 extern "C" int bchfft_dev_upload(int device, void *d_dst, const void *h_src, size_t bytes)
 {
   BCHFFT_CUDA_TRY(cudaSetDevice(device));

@@ -129,6 +129,12 @@ int bchfft_dev_free(int device, void *p);
 int bchfft_dev_upload(int device, void *d_dst, const void *h_src, size_t bytes);
 int bchfft_dev_download(int device, void *h_dst, const void *d_src, size_t bytes);
 
+/* page-locked host memory: buffers handed to the *_host entry points should come from here, so
+ * that the copy-in / decode / copy-out lanes really overlap (pageable memory is staged by the
+ * driver and the copies serialise).  Usable from any thread; freed with bchfft_pinned_free. */
+int bchfft_pinned_alloc(size_t bytes, void **out);
+int bchfft_pinned_free(void *p);
+
 /* launch counter: number of kernels this library has launched since the last reset
  * (bench.py reports it as gpu_launches) */
 uint64_t bchfft_launch_count(void);

@@ -396,3 +396,35 @@ def test_host_only_check_fft_polynomials(emu_libs, port, m):
     bad = div.copy()
     bad[m - 1, 1] ^= 1
     assert L.check_fft_polynomials(*args(bad)) == 0
+
+
+def test_emu_bchstream_cli(emu_libs, port, tmp_path):
+    """host/bchstream: packed codewords stdin -> stdout through bch_decode_batch,
+    several batches incl. a ragged last one; output, ok and corrected equal the oracle's"""
+    import subprocess
+    subprocess.run(["make", "-C", ROOT, "stream-emu"], check=True, stdout=subprocess.DEVNULL)
+    n, t = 255, 4
+    pc = port.code(n, t)
+    rng = np.random.default_rng(77)
+    B, W = 70, 4
+    words = np.zeros((B, W), np.uint64)
+    for i in range(B):
+        bits = rng.integers(0, 2, n - pc.gen_degree, dtype=np.uint8)
+        w = pc.encode(bits)
+        ne = int(rng.integers(0, t + 3))
+        for p in rng.choice(n, ne, replace=False):
+            w[p // 64] ^= np.uint64(1) << np.uint64(p % 64)
+        words[i] = w
+    ok_w, corr_w, out_w = pc.decode_batch(words.copy())
+    status = tmp_path / "status.bin"
+    exe = os.path.join(ROOT, "host", "bchstream_emu")
+    r = subprocess.run([exe, str(n), str(t), "-b", "32", "-s", str(status)], input=words.tobytes(),
+                       capture_output=True, check=True)
+    got = np.frombuffer(r.stdout, np.uint64).reshape(B, W)
+    assert (got == out_w).all()
+    rec = np.fromfile(status, np.uint32).reshape(B, 2)
+    assert (rec[:, 0] == ok_w).all() and (rec[:, 1] == corr_w).all()
+    assert b"70 codewords" in r.stderr
+    # truncated input: the stray bytes are reported, the exit code is non-zero
+    r = subprocess.run([exe, str(n), str(t)], input=words.tobytes()[:-3], capture_output=True)
+    assert r.returncode != 0 and len(r.stdout) == (B - 1) * W * 8

@@ -343,3 +343,33 @@ def test_prebuilt_reference_demos_pass(gpu_libs):
         assert out.returncode == 0 and "Test successful" in out.stdout, out.stdout[-500:]
     out = subprocess.run([fftdemo], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "Test successful!" in out.stdout, out.stdout[-800:]
+
+
+def test_bchstream_cli_round_trip(gpu_libs, port, tmp_path):
+    """host/bchstream (streaming decoder CLI) on the GPU: 100000 words of the
+    (8191, 16) code through stdin/stdout in ragged batches; corrected words, ok and corrected equal
+    bch_decode_batch's, and the first 2000 equal the oracle's"""
+    exe = os.path.join(ROOT, "host", "bchstream")
+    assert os.path.exists(exe), "host/bchstream missing: run `make stream` (or __graft_entry__.build())"
+    _, host = gpu_libs
+    n, t, B = 8191, 16, 100_000
+    code = host.bch_gen_code(n, 2 * t + 1)
+    k = code.data_bits
+    dw = (k + 63) // 64
+    words = code.encode_batch(synth.splitmix64(0x57, B * dw).reshape(B, dw), k)
+    rng = np.random.default_rng(0x57)
+    nerr = rng.integers(0, t + 3, B)                      # up to t+2 errors: failures included
+    for e in range(1, t + 3):
+        rows = np.nonzero(nerr >= e)[0]
+        band = n // (t + 2)
+        pos = (e - 1) * band + rng.integers(0, band, rows.size)   # bit 0 allowed (reference quirk)
+        words[rows, pos // 64] ^= np.uint64(1) << (pos % 64).astype(np.uint64)
+    ok, corr, out = code.decode_batch(words.copy())
+    status = tmp_path / "status.bin"
+    r = subprocess.run([exe, str(n), str(t), "-b", "30000", "-s", str(status)], input=words.tobytes(),
+                       capture_output=True, check=True, timeout=600)
+    got = np.frombuffer(r.stdout, np.uint64).reshape(B, -1)
+    rec = np.fromfile(status, np.uint32).reshape(B, 2)
+    assert (got == out).all() and (rec[:, 0] == ok).all() and (rec[:, 1] == corr).all()
+    ok_w, corr_w, out_w = port.code(n, t).decode_batch(words[:2000].copy())
+    assert (got[:2000] == out_w).all() and (rec[:2000, 0] == ok_w).all() and (rec[:2000, 1] == corr_w).all()
