@@ -428,3 +428,52 @@ def test_emu_bchstream_cli(emu_libs, port, tmp_path):
     # truncated input: the stray bytes are reported, the exit code is non-zero
     r = subprocess.run([exe, str(n), str(t)], input=words.tobytes()[:-3], capture_output=True)
     assert r.returncode != 0 and len(r.stdout) == (B - 1) * W * 8
+
+
+def test_emu_host_api_concurrent_callers(emu_libs, port):
+    """the reference is re-entrant (threading row): concurrent callers with distinct
+    buffers and shared read-only TfiniteField / TbchCode must get the single-threaded answers.
+    Four threads mix bch_decode_batch, bch_decode and additive FFT calls on two codes."""
+    import threading
+    _, host = emu_libs
+    rng = np.random.default_rng(4242)
+    jobs = []
+    for n, t in ((255, 4), (1023, 6)):
+        code = host.bch_gen_code(n, 2 * t + 1)
+        pc = port.code(n, t)
+        W = code.words
+        words = np.zeros((40, W), np.uint64)
+        for i in range(40):
+            w = pc.encode(rng.integers(0, 2, n - pc.gen_degree, dtype=np.uint8))
+            for p in rng.choice(n, int(rng.integers(0, t + 2)), replace=False):
+                w[p // 64] ^= np.uint64(1) << np.uint64(p % 64)
+            words[i] = w
+        jobs.append((code, words, pc.decode_batch(words.copy())))
+    f = host.create_binary_finite_field(10)
+    poly = rng.integers(0, 1 << 10, 1 << 10, dtype=np.uint32)
+    want_fft = port.additive_fft(10, poly, (1 << 10) - 1)[0]
+    errors = []
+
+    def worker(k):
+        try:
+            for rep in range(6):
+                code, words, (ok_w, corr_w, out_w) = jobs[(k + rep) % 2]
+                if (k + rep) % 3 == 0:
+                    got = f.evaluate_polynomial_additive_FFT(poly.copy(), (1 << 10) - 1)
+                    assert (got == want_fft).all()
+                elif k % 2:
+                    ok, corr, out = code.decode_batch(words)
+                    assert (ok == ok_w).all() and (corr == corr_w).all() and (out == out_w).all()
+                else:
+                    for i in range(0, 40, 7):
+                        o, c, w = code.decode(words[i])
+                        assert (o, c) == (int(ok_w[i]), int(corr_w[i])) and (w == out_w[i]).all()
+        except Exception as e:   # noqa: BLE001 - reported to the main thread
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors

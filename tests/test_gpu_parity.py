@@ -373,3 +373,52 @@ def test_bchstream_cli_round_trip(gpu_libs, port, tmp_path):
     assert (got == out).all() and (rec[:, 0] == ok).all() and (rec[:, 1] == corr).all()
     ok_w, corr_w, out_w = port.code(n, t).decode_batch(words[:2000].copy())
     assert (got[:2000] == out_w).all() and (rec[:2000, 0] == ok_w).all() and (rec[:2000, 1] == corr_w).all()
+
+
+def test_host_api_concurrent_callers(gpu_libs, port):
+    """re-entrancy of the drop-in library (threading row) on the real device: four
+    threads with distinct buffers share one TbchCode / TfiniteField and mix bch_decode_batch,
+    bch_decode and additive FFT calls; every answer equals the single-threaded one"""
+    import threading
+    _, host = gpu_libs
+    n, t, B = 8191, 16, 3000
+    code = host.bch_gen_code(n, 2 * t + 1)
+    k = code.data_bits
+    dw = (k + 63) // 64
+    words = code.encode_batch(synth.splitmix64(0x7C, B * dw).reshape(B, dw), k)
+    rng = np.random.default_rng(0x7C)
+    nerr = rng.integers(0, t + 3, B)
+    for e in range(1, t + 3):
+        rows = np.nonzero(nerr >= e)[0]
+        band = n // (t + 2)
+        pos = (e - 1) * band + rng.integers(0, band, rows.size)
+        words[rows, pos // 64] ^= np.uint64(1) << (pos % 64).astype(np.uint64)
+    ok_w, corr_w, out_w = code.decode_batch(words)
+    ok_o, corr_o, out_o = port.code(n, t).decode_batch(words[:300].copy())
+    assert (ok_w[:300] == ok_o).all() and (corr_w[:300] == corr_o).all() and (out_w[:300] == out_o).all()
+    f = host.create_binary_finite_field(13)
+    poly = rng.integers(0, 1 << 13, 1 << 13, dtype=np.uint32)
+    want_fft = port.additive_fft(13, poly, (1 << 13) - 1)[0]
+    errors = []
+
+    def worker(j):
+        try:
+            for rep in range(8):
+                if (j + rep) % 3 == 0:
+                    assert (f.evaluate_polynomial_additive_FFT(poly.copy(), (1 << 13) - 1) == want_fft).all()
+                elif j % 2:
+                    ok, corr, out = code.decode_batch(words)
+                    assert (ok == ok_w).all() and (corr == corr_w).all() and (out == out_w).all()
+                else:
+                    for i in range(j, B, 211):
+                        o, c, w = code.decode(words[i])
+                        assert (o, c) == (int(ok_w[i]), int(corr_w[i])) and (w == out_w[i]).all()
+        except Exception as e:   # noqa: BLE001 - reported to the main thread
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(j,)) for j in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
