@@ -512,6 +512,119 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
     for (uint32_t j = sub; j <= upto; j += LPC) e[j] = C[j * cs];
 }
 
+// ---- Berlekamp-Massey, one CTA per codeword ---------------------------------------------------
+// Same recurrence and buffer rotation as k_bm (bch.c:328-404), for FEW codewords with LARGE t
+// (the reference's single decode at n = 65535, t = 1000: 2t iterations of up to t multiply-adds are
+// 2*10^6 dependent steps for one thread).  Here the blockDim.x threads of a CTA split the
+// coefficient index j of both inner loops; per iteration one XOR reduction (discrepancy) and, when
+// the degrees tie, one max reduction (degree of the new C) go through shared memory.  All control
+// state (L, gap, degrees, buffer roles) is replicated in every thread and stays uniform because it
+// only depends on reduced values read behind a barrier.  The three coefficient buffers and the
+// syndromes live in shared memory: dynamic smem = (4 d + 3) words.  Reduction cells rotate over
+// three slots: the cell of iteration i + 2 is cleared by thread 0 after the barrier of iteration i,
+// and nobody adds to it before the barrier of iteration i + 1.
+template <int M>
+__global__ void k_bm_wide(const uint32_t *__restrict__ syn, const int32_t *__restrict__ flag, uint32_t d,
+                          uint32_t batch, const uint32_t *__restrict__ gexp, const uint32_t *__restrict__ glog,
+                          uint32_t *__restrict__ elp, uint32_t *__restrict__ Lout, uint32_t elp_limit)
+{
+  const uint32_t order = (1u << M) - 1u;
+  BCHFFT_DYN_SMEM(uint32_t, poly);
+  __shared__ uint32_t sh_disc[3];
+  __shared__ int sh_last[3];
+  const uint32_t cw = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  if (cw >= batch) return;
+  uint32_t *A = poly, *B = A + (d + 1u), *C = B + (d + 1u), *sc = C + (d + 1u);
+  for (uint32_t j = tid; j < 3u * (d + 1u); j += nt) poly[j] = 0u;
+  for (uint32_t j = tid; j < d; j += nt) sc[j] = syn[(size_t)cw * d + j];
+  if (tid < 3u) {
+    sh_disc[tid] = 0u;
+    sh_last[tid] = -1;
+  }
+  __syncthreads();
+  if (tid == 0u) {
+    B[0] = 1u;
+    C[0] = 1u;
+  }
+  __syncthreads();
+  auto add_disc = [&](uint32_t slot, uint32_t v) {
+#ifndef BCHFFT_EMU
+    v = __reduce_xor_sync(0xFFFFFFFFu, v);
+    if ((tid & 31u) == 0u && v) atomicXor(&sh_disc[slot], v);
+#else
+    if (v) atomicXor(&sh_disc[slot], v);
+#endif
+  };
+  auto add_last = [&](uint32_t slot, int v) {
+#ifndef BCHFFT_EMU
+    v = __reduce_max_sync(0xFFFFFFFFu, v);
+    if ((tid & 31u) == 0u && v >= 0) atomicMax(&sh_last[slot], v);
+#else
+    if (v >= 0) atomicMax(&sh_last[slot], v);
+#endif
+  };
+  uint32_t L = 0;
+  if (flag[cw]) {
+    uint32_t degA = 0, degB = 0, degC = 0, gap = 1, inv_b_log = 0, slot = 0;
+    for (uint32_t i = 0; i + 1 < d; ++i, slot = slot == 2u ? 0u : slot + 1u) {
+      uint32_t part = 0u;
+      for (uint32_t j = 1u + tid; j <= degC; j += nt) part ^= gf_mul<M>(C[j], sc[i + 1u - j]);
+      add_disc(slot, part);
+      __syncthreads();
+      const uint32_t disc = sh_disc[slot] ^ sc[i + 1u];
+      const uint32_t clear = slot == 0u ? 2u : slot - 1u;   // = (slot + 2) % 3: the cell of iteration i + 2
+      if (tid == 0u) {
+        sh_disc[clear] = 0u;
+        sh_last[clear] = -1;
+      }
+      if (!disc) {
+        gap++;
+        continue;
+      }
+      const uint32_t dlog = glog[disc];
+      uint32_t sl = dlog + inv_b_log;
+      if (sl >= order) sl -= order;
+      const uint32_t scale = gexp[sl];
+      const uint32_t hiB = degB + gap;
+      const uint32_t top = hiB > degC ? hiB : degC;
+      int last_nz = -1;
+      for (uint32_t j = tid; j <= top; j += nt) {
+        const uint32_t bv = (j >= gap && j <= hiB) ? B[j - gap] : 0u;
+        const uint32_t cv = j <= degC ? C[j] : 0u;
+        const uint32_t v = gf_mul<M>(bv, scale) ^ cv;
+        if (j >= gap && j <= degC && v) last_nz = (int)j;
+        A[j] = v;
+      }
+      if (degC != hiB) {
+        degA = top;
+        __syncthreads();   // the new coefficients are visible before the next discrepancy
+      } else {
+        add_last(slot, last_nz);
+        __syncthreads();
+        const int ln = sh_last[slot];
+        if (ln >= 0) degA = (uint32_t)ln;   // otherwise degA keeps its previous value (bch.c:379-384)
+      }
+      if (2u * L <= i) {
+        L = i + 1u - L;
+        degB = degC;
+        uint32_t *t = B; B = C; C = t;
+        inv_b_log = order - dlog;
+        gap = 1;
+      } else {
+        gap++;
+      }
+      { uint32_t *t = C; C = A; A = t; }
+      degC = degA;
+    }
+  }
+  __syncthreads();
+  if (tid == 0u) Lout[cw] = L;
+  uint32_t *e = elp + (size_t)cw * (d + 1);
+  const uint32_t upto = elp_limit >= d ? d : (L <= elp_limit ? L : 0u);
+  if (elp_limit >= d || (L >= 1u && L <= elp_limit))
+    for (uint32_t j = tid; j <= upto; j += nt) e[j] = C[j];
+}
+
 // ---- root search ----------------------------------------------------------------------------
 // The error locator of every codeword is evaluated at all 2^M field points with the truncated
 // additive FFT (the device counterpart of bch.c:406-490's FFT path, with the reference's

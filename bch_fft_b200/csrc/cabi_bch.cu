@@ -163,6 +163,15 @@ static const unsigned kBmThreads = 256;
 static constexpr int kBmLpc = BCHFFT_BM_LPC;      // lanes per codeword of the shared-memory kernel
 #endif
 
+// Few codewords with a long recurrence (single decode at n = 65535, t = 1000): one CTA per codeword
+// (k_bm_wide) instead of one thread.  Break-even is at about 16 t codewords.
+static bool bm_wide(const bchfft_code *c, size_t cnt)
+{
+  const char *wenv = getenv("BCHFFT_BM_WIDE");
+  const size_t smem_w = sizeof(uint32_t) * ((size_t)4 * c->d + 3u);
+  return c->t >= 24u && cnt <= (size_t)16 * c->t && smem_w <= (size_t)200 * 1024 && !(wenv && atoi(wenv) == 0);
+}
+
 // true when launch_bm takes the shared-memory kernel, which can also finish the syndromes itself
 template <int M>
 static bool bm_in_smem(const bchfft_code *c, unsigned *nt_out, size_t *smem_out)
@@ -184,6 +193,16 @@ static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t 
 {
   unsigned nt;
   size_t smem;
+  if (!fused && bm_wide(c, cnt)) {
+    const size_t smem_w = sizeof(uint32_t) * ((size_t)4 * c->d + 3u);
+    unsigned ntw = ((c->t + 1u + 31u) / 32u) * 32u;
+    ntw = ntw < 64u ? 64u : (ntw > 1024u ? 1024u : ntw);
+    BCHFFT_ENSURE_SMEM(k_bm_wide<M>, c->f->device, smem_w);
+    BCHFFT_RUN(k_bm_wide<M>, dim3((unsigned)cnt), dim3(ntw), smem_w, st, (const uint32_t *)s.syn,
+               (const int32_t *)s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
+               (const uint32_t *)c->f->d_log, s.elp, s.L, elp_limit);
+    return BCHFFT_OK;
+  }
   if (bm_in_smem<M>(c, &nt, &smem)) {
     constexpr bool kSm = M <= 14;
     constexpr int kLpc = kSm ? kBmLpc : 1;
@@ -331,7 +350,7 @@ static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words
     size_t smem_bm;
     const char *fenv = getenv("BCHFFT_BM_FUSED");
     const bool bm_sm = bm_in_smem<M>(c, &nt_bm, &smem_bm);
-    const bool fused = bm_sm && !(fenv && atoi(fenv) == 0);
+    const bool fused = bm_sm && !bm_wide(c, cnt) && !(fenv && atoi(fenv) == 0);
     BCHFFT_CUDA_TRY(cudaMemsetAsync(w.scratch.p, 0, zero_bytes(c, cnt, M, !bm_sm), st));
     if ((rc = launch_syndrome<M>(c, wp, cnt, s, st, !fused))) return rc;
     if ((rc = launch_bm<M>(c, cnt, s, st, fused, c->t))) return rc;

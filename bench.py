@@ -502,7 +502,78 @@ def run_extras(args, rank, world, local_rank, lib, host, barrier, max_over_ranks
                      "ms_per_step": total_ms / steps, "m": m, "batch_per_gpu": B}
         dfield.close()
         del d_in, d_out
+    if rank == 0 and world == 1:
+        out["single_call"] = single_call_latency(host, args)
     return out
+
+
+def single_call_latency(host, args):
+    """BASELINE configs[0] / configs[1]: latency of ONE call of the reference's
+    single-item entry points with host buffers -- evaluate_polynomial_additive_FFT over GF(2^16)
+    and bch_decode at n = 65535 with t errors -- through the drop-in library (GPU, copies
+    included) and through the unmodified reference (oracle/_ref, one thread), checked equal."""
+    import ctypes as C
+    from oracle import pyoracle
+    ref = pyoracle.Ref() if pyoracle.ref_available() else None
+    u32p, ulp = C.POINTER(C.c_uint32), C.POINTER(C.c_ulong)
+    res = {}
+    reps = 20
+    # ---- one additive FFT, full degree, GF(2^16)
+    m, n = 16, 1 << 16
+    f = host.create_binary_finite_field(m)
+    poly = synth.random_polys(m, 1, 0xC1)[0]
+    want = None
+    cpu_ms = None
+    if ref is not None:
+        ts = []
+        for _ in range(3):
+            want, dt = ref.additive_fft_batch_mt(m, poly[None, :], n - 1, 1)
+            ts.append(dt)
+        cpu_ms = 1e3 * min(ts)
+    out = np.zeros(n, np.uint32)
+    ts = []
+    for _ in range(3 + reps):
+        work = poly.copy()
+        t0 = time.perf_counter()
+        host.lib.evaluate_polynomial_additive_FFT(C.byref(f.c), work.ctypes.data_as(u32p),
+                                                  out.ctypes.data_as(u32p), n - 1)
+        ts.append(time.perf_counter() - t0)
+    ts = sorted(ts[3:])
+    res["additive_fft_gf2_16"] = {"gpu_ms_median": 1e3 * ts[len(ts) // 2], "gpu_ms_min": 1e3 * ts[0],
+                                  "reference_cpu_ms": cpu_ms,
+                                  "equal": None if want is None else bool((out[: n - 1] == want[0]).all())}
+    # ---- one decode at n = 65535, exactly t errors
+    for t in (100, 1000):
+        length = 65535
+        code = host.bch_gen_code(length, 2 * t + 1)
+        word = code.encode((synth.splitmix64(0xC2 + t, code.data_bits) & np.uint64(1)).astype(np.uint32))
+        rng = np.random.default_rng(0xC2 + t)
+        for p in rng.choice(np.arange(1, length), t, replace=False):
+            word[p // 64] ^= np.uint64(1) << np.uint64(p % 64)
+        cpu_ms = None
+        ref_out = None
+        if ref is not None:
+            rc = ref.code(length, t)
+            ts = []
+            for _ in range(3):
+                ok_r, corr_r, w_r, dt = rc.decode_batch_mt(word[None, :], 1)
+                ts.append(dt)
+            cpu_ms = 1e3 * min(ts)
+            ref_out = (int(ok_r[0]), int(corr_r[0]), w_r[0])
+        ts = []
+        corr = C.c_uint32(0)
+        for _ in range(3 + reps):
+            work = word.copy()
+            t0 = time.perf_counter()
+            ok = host.lib.bch_decode(C.byref(code.c), work.ctypes.data_as(ulp), None, C.byref(corr))
+            ts.append(time.perf_counter() - t0)
+        ts = sorted(ts[3:])
+        res[f"bch_decode_n65535_t{t}"] = {
+            "gpu_ms_median": 1e3 * ts[len(ts) // 2], "gpu_ms_min": 1e3 * ts[0], "reference_cpu_ms": cpu_ms,
+            "ok": int(ok), "corrected": int(corr.value),
+            "equal": None if ref_out is None else bool(
+                ref_out[0] == int(ok) and ref_out[1] == int(corr.value) and (ref_out[2] == work).all())}
+    return res
 
 
 _RESULT_FD = None

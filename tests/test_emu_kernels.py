@@ -477,3 +477,46 @@ def test_emu_host_api_concurrent_callers(emu_libs, port):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+def _wide_bm_case(cabi, host, port, n, t, B, seed):
+    """few codewords, large t: launch_bm picks k_bm_wide (one CTA per codeword); same answers as
+    the one-thread-per-codeword kernel (BCHFFT_BM_WIDE=0) and as the oracle, >t errors included"""
+    code = host.bch_gen_code(n, 2 * t + 1)
+    pc = port.code(n, t)
+    rng = np.random.default_rng(seed)
+    words = np.zeros((B, code.words), np.uint64)
+    for i in range(B):
+        w = pc.encode(rng.integers(0, 2, n - pc.gen_degree, dtype=np.uint8))
+        ne = [0, 1, t, t + 1, t + 7][i] if i < 5 else int(rng.integers(0, t + 3))
+        for p in rng.choice(n, ne, replace=False):
+            w[p // 64] ^= np.uint64(1) << np.uint64(p % 64)
+        words[i] = w
+    want = pc.decode_batch(words.copy())
+    names = {}
+
+    def run():
+        names["got"] = code.decode_batch(words)
+    prof = _lib.profile(cabi, run)
+    assert any(k.startswith("k_bm_wide") for k in prof), sorted(prof)
+    for a, b in zip(names["got"], want):
+        assert (a == b).all()
+    os.environ["BCHFFT_BM_WIDE"] = "0"
+    try:
+        prof = _lib.profile(cabi, run)
+    finally:
+        del os.environ["BCHFFT_BM_WIDE"]
+    assert not any(k.startswith("k_bm_wide") for k in prof) and any(k.startswith("k_bm") for k in prof)
+    for a, b in zip(names["got"], want):
+        assert (a == b).all()
+    # stage-level entry point (bch_compute_elp): L and the whole locator buffer
+    for i in (2, 3, B - 1):
+        _, syn, _ = pc.syndrome(words[i])
+        L_w, elp_w = pc.elp(syn)
+        L_g, elp_g = code.compute_elp(syn)
+        assert L_g == L_w and (np.asarray(elp_g)[: L_w + 1] == elp_w).all()
+
+
+def test_emu_wide_berlekamp_massey(emu_libs, port):
+    cabi, host = emu_libs
+    _wide_bm_case(cabi, host, port, 8191, 64, 9, 640)

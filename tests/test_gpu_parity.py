@@ -422,3 +422,11 @@ def test_host_api_concurrent_callers(gpu_libs, port):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("n,t,B", [(8191, 64, 12), (8191, 200, 7), (65535, 100, 6), (65535, 1000, 5)])
+def test_wide_berlekamp_massey(gpu_libs, port, n, t, B):
+    """k_bm_wide (one CTA per codeword; single decodes with large t) against k_bm and the oracle"""
+    from tests.test_emu_kernels import _wide_bm_case
+    cabi, host = gpu_libs
+    _wide_bm_case(cabi, host, port, n, t, B, 1000 + t)
