@@ -293,6 +293,56 @@ __global__ void k_syn_finish(const uint32_t *__restrict__ acc, const uint32_t *_
   flag[cw] = any ? 1 : 0;
 }
 
+// ---- syndromes of few long codewords through the additive FFT ---------------------------------
+// The reference's own choice for large d (bch.c:278-292): unpack the word to one coefficient per
+// bit, evaluate it at every x^i with one additive FFT, the syndromes are entries 0 .. d-1.  The
+// LFSR kernels above cost (positions x classes) per slab even when the slab holds one codeword;
+// for a handful of codewords with many classes the transform is cheaper (host rule: syn_fft()).
+// k_unpack_bits: grid = (ceil(n / 256), batch); coef[cw][p] = bit p of the word, 0 for p >= length.
+__global__ void k_unpack_bits(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32_t length,
+                              uint32_t n, uint32_t *__restrict__ coef)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, cw = blockIdx.y;
+  if (p >= n) return;
+  uint32_t v = 0u;
+  if (p < length) v = (words32[(size_t)cw * words32_per_cw + (p >> 5)] >> (p & 31u)) & 1u;
+  coef[(size_t)cw * n + p] = v;
+}
+
+// One CTA per codeword: syn[cw][j] = P(x^j) from the transform for j = 1 .. d-1, syn[cw][0] = the
+// reference's method-dependent entry (XOR of the word bits selected by vbits, see k_syndrome),
+// flag[cw] = any of them non-zero (bch.c:317-324).
+__global__ void k_syn_from_fft(const uint32_t *__restrict__ res, uint32_t res_stride,
+                               const uint32_t *__restrict__ words32, uint32_t words32_per_cw,
+                               const uint32_t *__restrict__ vbits, uint32_t d,
+                               uint32_t *__restrict__ syn, int32_t *__restrict__ flag)
+{
+  __shared__ uint32_t s_par, s_any;
+  const uint32_t cw = blockIdx.x;
+  if (threadIdx.x == 0) {
+    s_par = 0u;
+    s_any = 0u;
+  }
+  __syncthreads();
+  uint32_t par = 0u;
+  for (uint32_t w = threadIdx.x; w < words32_per_cw; w += blockDim.x)
+    par ^= words32[(size_t)cw * words32_per_cw + w] & vbits[w];
+  par = (uint32_t)__popc(par) & 1u;
+  if (par) atomicXor(&s_par, 1u);
+  uint32_t any = 0u;
+  for (uint32_t j = 1u + threadIdx.x; j < d; j += blockDim.x) {
+    const uint32_t v = res[(size_t)cw * res_stride + j];
+    syn[(size_t)cw * d + j] = v;
+    any |= v;
+  }
+  if (any) atomicOr(&s_any, 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    syn[(size_t)cw * d] = s_par;
+    flag[cw] = (s_any | s_par) ? 1 : 0;
+  }
+}
+
 // ---- Berlekamp-Massey -----------------------------------------------------------------------
 // One thread per codeword, faithful to bch.c:328-404 including the rotation of the three
 // coefficient buffers (so that C[deg C + 1 .. L], which the reference leaves stale, is

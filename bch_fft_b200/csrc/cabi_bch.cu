@@ -26,6 +26,7 @@ struct bchfft_code {
   // lanes of the pipelined host entry point (copy-in / decode / copy-out overlap)
   struct WorkSet {
     bchfft::DeviceBuffer scratch, fwd_buf, words, ok, corr;
+    bchfft::DeviceBuffer fft_ws, fft_io;   // syndromes through the additive FFT (few long codewords)
     cudaStream_t stream = nullptr;
     int descs_t = -1, descs_kmax = -1;   // butterfly descriptors currently uploaded in fwd_buf
     void *descs_at = nullptr;
@@ -121,11 +122,33 @@ static const int kNtSyn = 32, kNtLoc = 32;
 static const int kNtSyn = BCHFFT_NT_SYN, kNtLoc = BCHFFT_NT_LOC;
 #endif
 
+// Few codewords, many syndrome classes: one additive FFT per word (the reference's FFT method,
+// bch.c:278-292) instead of positions x classes LFSR steps on a slab that is nearly empty.
+static bool syn_fft(const bchfft_code *c, size_t cnt)
+{
+  const char *env = getenv("BCHFFT_SYN_FFT");
+  return cnt <= 64 && c->nodd >= 48u && c->f->m >= 8u && !(env && atoi(env) == 0);
+}
+
 template <int M>
-static int launch_syndrome(bchfft_code *c, const uint64_t *d_words, size_t cnt, const Scratch &s,
-                           cudaStream_t st, bool finish = true)
+static int launch_syndrome(bchfft_code *c, bchfft_code::WorkSet &w, const uint64_t *d_words, size_t cnt,
+                           const Scratch &s, cudaStream_t st, bool finish = true)
 {
   const unsigned ns = (unsigned)((cnt + 31) / 32);
+  if (finish && syn_fft(c, cnt)) {
+    const uint32_t n = c->f->n;
+    int rc = w.fft_io.reserve((size_t)2 * cnt * n * sizeof(uint32_t));
+    if (rc) return rc;
+    uint32_t *coef = (uint32_t *)w.fft_io.p, *res = coef + cnt * (size_t)n;
+    BCHFFT_RUN(k_unpack_bits, dim3((n + 255u) / 256u, (unsigned)cnt), dim3(256), 0, st,
+               (const uint32_t *)d_words, c->wpc * 2u, c->length, n, coef);
+    const uint32_t terms = c->length < n - 1u ? c->length : n - 1u;
+    if ((rc = bchfft_additive_fft_dev_ws(c->f, w.fft_ws, coef, n, res, n, nullptr, 0, terms, cnt, (void *)st)))
+      return rc;
+    BCHFFT_RUN(k_syn_from_fft, dim3((unsigned)cnt), dim3(256), 0, st, (const uint32_t *)res, n,
+               (const uint32_t *)d_words, c->wpc * 2u, (const uint32_t *)c->d_vbits, c->d, s.syn, s.flag);
+    return BCHFFT_OK;
+  }
   const char *penv = getenv("BCHFFT_SYN_P");
   if (c->syn_p && !(penv && atoi(penv) == 0)) {
     const size_t smem_p = 2u * sizeof(uint32_t) * ((size_t)((c->f->order + 31u) / 32u) * 33u + (size_t)c->nodd * M);
@@ -352,7 +375,7 @@ static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words
     const bool bm_sm = bm_in_smem<M>(c, &nt_bm, &smem_bm);
     const bool fused = bm_sm && !bm_wide(c, cnt) && !(fenv && atoi(fenv) == 0);
     BCHFFT_CUDA_TRY(cudaMemsetAsync(w.scratch.p, 0, zero_bytes(c, cnt, M, !bm_sm), st));
-    if ((rc = launch_syndrome<M>(c, wp, cnt, s, st, !fused))) return rc;
+    if ((rc = launch_syndrome<M>(c, w, wp, cnt, s, st, !fused))) return rc;
     if ((rc = launch_bm<M>(c, cnt, s, st, fused, c->t))) return rc;
     if ((rc = launch_locate<M>(c, w, cnt, s, c->t, st))) return rc;
     BCHFFT_RUN(k_correct, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, wp, c->wpc,
@@ -634,6 +657,8 @@ extern "C" void bchfft_code_destroy(bchfft_code *c)
     w.words.release();
     w.ok.release();
     w.corr.release();
+    w.fft_ws.release();
+    w.fft_io.release();
     if (w.stream) cudaStreamDestroy(w.stream);
   }
   delete c;
@@ -826,7 +851,7 @@ static int syndrome_stage(bchfft_code *c, const uint64_t *words, size_t batch, u
     BCHFFT_CUDA_TRY(cudaMemsetAsync(c->work[0].scratch.p, 0, zero_bytes(c, cnt, M), st));
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(c->work[0].words.p, words + i0 * c->wpc, cnt * cw_bytes,
                                     cudaMemcpyHostToDevice, st));
-    if ((rc = launch_syndrome<M>(c, (const uint64_t *)c->work[0].words.p, cnt, s, st))) return rc;
+    if ((rc = launch_syndrome<M>(c, c->work[0], (const uint64_t *)c->work[0].words.p, cnt, s, st))) return rc;
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(syndromes + i0 * c->d, s.syn, cnt * c->d * 4, cudaMemcpyDeviceToHost, st));
     if (flags) BCHFFT_CUDA_TRY(cudaMemcpyAsync(flags + i0, s.flag, cnt * 4, cudaMemcpyDeviceToHost, st));
     BCHFFT_CUDA_TRY(cudaStreamSynchronize(st));

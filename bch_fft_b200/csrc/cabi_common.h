@@ -89,3 +89,9 @@ struct bchfft_field {
   // multiplicative FFT state (lazily built)
   void *mfft = nullptr;
 };
+
+// bchfft_additive_fft_dev with an explicit slab workspace (cabi_fft.cu); the decode pipeline uses it
+// with a workspace of its own lane for the syndromes of few long codewords
+int bchfft_additive_fft_dev_ws(bchfft_field *f, bchfft::DeviceBuffer &ws, const uint32_t *d_polys, size_t poly_stride,
+                               uint32_t *d_results, size_t result_stride, uint32_t *d_natural,
+                               size_t natural_stride, uint32_t num_terms, size_t batch, void *stream);

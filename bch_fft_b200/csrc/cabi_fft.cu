@@ -181,7 +181,8 @@ static int fft_run(bchfft_field *f, DeviceBuffer &ws, const uint32_t *d_polys, s
 
 using namespace bchfft;
 
-static int additive_fft_dev_ws(bchfft_field *f, bchfft::DeviceBuffer &ws, const uint32_t *d_polys, size_t poly_stride,
+// also called by the decode pipeline (cabi_bch.cu: syndromes of few long codewords), declared in cabi_common.h
+int bchfft_additive_fft_dev_ws(bchfft_field *f, bchfft::DeviceBuffer &ws, const uint32_t *d_polys, size_t poly_stride,
                                        uint32_t *d_results, size_t result_stride, uint32_t *d_natural,
                                        size_t natural_stride, uint32_t num_terms, size_t batch,
                                        void *stream)
@@ -219,7 +220,7 @@ extern "C" int bchfft_additive_fft_dev(bchfft_field *f, const uint32_t *d_polys,
     set_error("bchfft_additive_fft_dev: null argument");
     return BCHFFT_ERR_ARG;
   }
-  return additive_fft_dev_ws(f, f->ws, d_polys, poly_stride, d_results, result_stride, d_natural,
+  return bchfft_additive_fft_dev_ws(f, f->ws, d_polys, poly_stride, d_results, result_stride, d_natural,
                              natural_stride, num_terms, batch, stream);
 }
 
@@ -255,7 +256,7 @@ extern "C" int bchfft_additive_fft_host(bchfft_field *f, const uint32_t *polys, 
                                       (size_t)n * 4, cnt, cudaMemcpyHostToDevice, l.stream));
     uint32_t *d_res = results ? (uint32_t *)l.out.p : nullptr;
     uint32_t *d_nat = natural ? (uint32_t *)l.aux.p : nullptr;
-    rc = additive_fft_dev_ws(f, l.ws, d_in, n, d_res, n, d_nat, n, num_terms, cnt, l.stream);
+    rc = bchfft_additive_fft_dev_ws(f, l.ws, d_in, n, d_res, n, d_nat, n, num_terms, cnt, l.stream);
     if (rc) return rc;
     // the reference never writes entry n-1 of po_result (additive_fft.c:20): copy n-1 per row
     if (results)

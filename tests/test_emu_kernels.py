@@ -499,19 +499,26 @@ def _wide_bm_case(cabi, host, port, n, t, B, seed):
         names["got"] = code.decode_batch(words)
     prof = _lib.profile(cabi, run)
     assert any(k.startswith("k_bm_wide") for k in prof), sorted(prof)
+    # t >= 48 (nodd >= 48) and at most 64 words: syndromes through one additive FFT per word
+    assert any(k.startswith("k_syn_from_fft") for k in prof) == (t >= 48), sorted(prof)
     for a, b in zip(names["got"], want):
         assert (a == b).all()
     os.environ["BCHFFT_BM_WIDE"] = "0"
+    os.environ["BCHFFT_SYN_FFT"] = "0"
     try:
         prof = _lib.profile(cabi, run)
     finally:
         del os.environ["BCHFFT_BM_WIDE"]
+        del os.environ["BCHFFT_SYN_FFT"]
     assert not any(k.startswith("k_bm_wide") for k in prof) and any(k.startswith("k_bm") for k in prof)
+    assert not any(k.startswith("k_syn_from_fft") for k in prof)
     for a, b in zip(names["got"], want):
         assert (a == b).all()
     # stage-level entry point (bch_compute_elp): L and the whole locator buffer
-    for i in (2, 3, B - 1):
-        _, syn, _ = pc.syndrome(words[i])
+    for i in (0, 1, 2, 3, B - 1):
+        flag_w, syn, _ = pc.syndrome(words[i])
+        flag_g, syn_g = code.eval_syndrome(words[i])          # bch_eval_syndrome incl. entry 0 and the flag
+        assert flag_g == flag_w and (syn_g == syn).all()
         L_w, elp_w = pc.elp(syn)
         L_g, elp_g = code.compute_elp(syn)
         assert L_g == L_w and (np.asarray(elp_g)[: L_w + 1] == elp_w).all()
