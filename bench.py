@@ -306,7 +306,7 @@ def run_ours(args, rank, world, local_rank):
                 "kernel_share_of_step": {k: round(v[0] / ksum, 4) for k, v in prof.items()},
                 "whole_step_frac": (B * CW_BYTES_8191 / (total_ms / args.steps * 1e-3) / 1e9) / peak_gbs,
                 "note": "integer/LOP3-bound bitsliced GF(2^13) arithmetic: the HBM fraction is low by "
-                        "construction, see DESIGN.md section 4 and profiles/r1q_ncu_summary_decode.txt "
+                        "construction, see DESIGN.md section 4 and profiles/r1v_ncu_summary_decode.txt "
                         "for the ALU-pipe and shared-memory utilisation"}
 
     # ---- end to end through the drop-in host API (pinned host buffers, copies timed) ---------
