@@ -12,6 +12,11 @@ HFLAGS := -std=gnu99 -O2 -fPIC -Wall -Wextra -I$(ROOT)include -I$(ROOT)host
 REF  ?= /root/reference
 
 all: cuda host oracle stream
+# where the reference tree exists (the build container) its demo sources are rebuilt against the
+# fresh libraries on every build, so the binaries that travel to the GPU box are never stale
+ifneq ($(wildcard $(REF)/bch/main.c),)
+all: demos
+endif
 cuda:
 	$(MAKE) -C $(CSRC) all
 emu: oracle

@@ -1212,6 +1212,67 @@ k_encode(const uint64_t *__restrict__ data, uint32_t dwords, uint32_t data_bits,
   }
 }
 
+// Any generator degree >= 64 (the (8191, 200) and (65535, 1000) codes: deg g = 2444, 15360): one
+// WARP per codeword.  The remainder S (deg g bits) lives in shared memory as NS = deg g / 64 + 1
+// words; the data polynomial is consumed 64 bits at a time from the top:
+//     S <- (S mod X^(dg-64)) X^64 + (top64(S) + chunk) X^dg  mod g
+//        = (S << 64, truncated to dg bits)  ^  sum_{k : bit k of u set} rows[k],  u = top64(S) ^ chunk,
+// rows[k] = X^(dg+k) mod g (64 rows of NS words, read through L1/L2).  u is warp-uniform, so the row
+// loop runs over its set bits only; lane l owns words l, l + 32, ...  Two copies of S alternate, one
+// __syncwarp per chunk.  grid = ceil(batch / warps per CTA), dynamic smem = warps * 2 * NS * 8.
+__global__ void __launch_bounds__(256)
+k_encode_wide(const uint64_t *__restrict__ data, uint32_t dwords, uint32_t data_bits, uint32_t dg,
+              const uint64_t *__restrict__ rows, uint64_t *__restrict__ cw_out, uint32_t wpc, uint32_t batch)
+{
+  BCHFFT_DYN_SMEM(uint64_t, sm);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const uint32_t cw = blockIdx.x * wpb + warp;
+  if (cw >= batch) return;   // whole warps leave; the kernel uses no CTA-wide barrier
+  const uint32_t NS = dg / 64u + 1u;
+  uint64_t *cur = sm + (size_t)warp * 2u * NS, *nxt = cur + NS;
+  const uint64_t *dsrc = data + (size_t)cw * dwords;
+  for (uint32_t w = lane; w < 2u * NS; w += 32u) cur[w] = 0ull;
+  __syncwarp();
+  const uint32_t hw = dg >> 6, r = dg & 63u;
+  const uint64_t hmask = r ? ((1ull << r) - 1ull) : 0ull;       // bits of word hw below dg
+  const uint32_t lastd = data_bits ? (data_bits - 1u) >> 6 : 0u;
+  auto dword = [&](uint32_t w) -> uint64_t {
+    if (!data_bits || w > lastd) return 0ull;
+    uint64_t x = dsrc[w];
+    if (w == lastd && ((data_bits - 1u) & 63u) != 63u) x &= (2ull << ((data_bits - 1u) & 63u)) - 1ull;
+    return x;
+  };
+  for (uint32_t c = data_bits ? lastd + 1u : 0u; c-- > 0;) {
+    // bits [dg-64, dg) of S
+    const uint64_t top = r ? ((cur[hw] << (64u - r)) | (cur[hw - 1u] >> r)) : cur[hw - 1u];
+    const uint64_t u = top ^ dword(c);
+    for (uint32_t w = lane; w < NS; w += 32u) {
+      uint64_t v = w ? cur[w - 1u] : 0ull;                       // S << 64
+      if (w == hw) v &= hmask;                                   // drop what moved to degree >= dg
+      uint64_t bits = u;
+      while (bits) {
+        const uint32_t k = (uint32_t)__ffsll((long long)bits) - 1u;
+        bits &= bits - 1ull;
+        v ^= rows[(size_t)k * NS + w];
+      }
+      nxt[w] = v;
+    }
+    __syncwarp();
+    uint64_t *t = cur; cur = nxt; nxt = t;
+  }
+  // codeword words: parity | data shifted up by dg
+  uint64_t *out = cw_out + (size_t)cw * wpc;
+  for (uint32_t j = lane; j < wpc; j += 32u) {
+    uint64_t v = j < NS ? cur[j] : 0ull;
+    if (data_bits && j >= hw) {
+      const uint32_t i = j - hw;
+      v |= dword(i) << r;
+      if (r && i >= 1u) v |= dword(i - 1u) >> (64u - r);
+    }
+    out[j] = v;
+  }
+}
+
 // ---- verdict + correction (bch.c:531-561) ---------------------------------------------------
 // ok = 1, corrected = 0 for a clean word; L > t -> ok = 0, corrected = 0; otherwise corrected =
 // #roots and the bits are flipped iff #roots == L.  Flips outside the packed array (only

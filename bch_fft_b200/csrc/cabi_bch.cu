@@ -18,8 +18,9 @@ struct bchfft_code {
   // field order; per class j^-1 mod order, per (class, chunk) the first permuted position, per
   // chunk the shift constants x^(q lc + b)
   uint32_t syn_p = 0;
-  // systematic encoder (k_encode): T[v] = v(X) X^deg(g) mod g, 256 rows of enc_nw 64-bit words
-  uint32_t enc_nw = 0;
+  // systematic encoder (k_encode): T[v] = v(X) X^deg(g) mod g, 256 rows of enc_nw 64-bit words;
+  // deg(g) > 2048 (enc_wide): rows X^(deg(g)+k) mod g, k < 64, of deg(g)/64+1 words (k_encode_wide)
+  uint32_t enc_nw = 0, enc_wide = 0;
   uint64_t *d_enc_table = nullptr;
   uint32_t *d_jinv = nullptr, *d_start = nullptr, *d_foldp = nullptr, *d_lcs = nullptr;
   // work sets: [0] serves the device-pointer and stage-level entry points, [1] .. [3] are the
@@ -27,9 +28,11 @@ struct bchfft_code {
   struct WorkSet {
     bchfft::DeviceBuffer scratch, fwd_buf, words, ok, corr;
     bchfft::DeviceBuffer fft_ws, fft_io;   // syndromes through the additive FFT (few long codewords)
+    // root-search pass descriptors: a buffer of their own, allocated once, so that a growing
+    // fwd_buf (DeviceBuffer::reserve frees and re-allocates) can never leave them stale
+    bchfft::DeviceBuffer descs;
     cudaStream_t stream = nullptr;
-    int descs_t = -1, descs_kmax = -1;   // butterfly descriptors currently uploaded in fwd_buf
-    void *descs_at = nullptr;
+    int descs_t = -1, descs_kmax = -1;   // (t, kmax) of the descriptors currently uploaded
   } work[4];
 };
 
@@ -273,22 +276,24 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
   const char *uenv = getenv("BCHFFT_LOCATE_U");
   const bool use_u = kmax <= kLocUMaxK && M >= 5 && M <= 22 && !(uenv && atoi(uenv) == 0);
   const unsigned ngroups = (unsigned)(cnt / 1024) + (unsigned)kmax + 1u;   // >= sum_K ceil(ceil(count_K/32)/32)
-  // work buffer: butterfly descriptors, bucket counts, bucket lists, forward values
   // descriptors: [0, kMaxBuckets] backward (butterfly) passes, [kMaxBuckets + 1, 2 kMaxBuckets + 1] forward passes
-  const size_t desc_bytes = (sizeof(PassDesc) * 2 * (kMaxBuckets + 1) + 255) & ~(size_t)255;
+  const size_t desc_bytes = sizeof(PassDesc) * 2 * (kMaxBuckets + 1);
+  // work buffer: bucket counts, bucket lists, forward values
   const size_t f_words = use_u ? (((size_t)ngroups << kmax) * M * 32u) : (((size_t)nvirt << kmax) * PS);
-  const size_t need = desc_bytes + ((kMaxBuckets + 1) + (size_t)(kMaxBuckets + 1) * cnt + f_words) * 4 + 256;
+  const size_t need = ((kMaxBuckets + 1) + (size_t)(kMaxBuckets + 1) * cnt + f_words) * 4 + 256;
   int rc = w.fwd_buf.reserve(need);
   if (rc) return rc;
-  PassDesc *d_descs = (PassDesc *)w.fwd_buf.p;
-  uint32_t *counts = (uint32_t *)((char *)w.fwd_buf.p + desc_bytes);
+  const bool fresh_descs = w.descs.p == nullptr;
+  if ((rc = w.descs.reserve(desc_bytes))) return rc;
+  PassDesc *d_descs = (PassDesc *)w.descs.p;
+  uint32_t *counts = (uint32_t *)w.fwd_buf.p;
   uint32_t *lists = counts + (kMaxBuckets + 1);
   // forward values are read and written as 16-byte vectors
   uint32_t *F = (uint32_t *)(((uintptr_t)(lists + (size_t)(kMaxBuckets + 1) * cnt) + 15) & ~(uintptr_t)15);
   std::vector<PassDesc> fwd(kMaxBuckets + 1), bwd(kMaxBuckets + 1);
   for (int K = 1; K <= kmax; K++) locate_descs(M, K, t, c->f->twist_free, fwd[K], bwd[K]);
-  if (w.descs_t != t || w.descs_kmax != kmax || w.descs_at != (void *)d_descs) {
-    // the descriptors only depend on (t, kmax): uploaded once per work buffer
+  if (fresh_descs || w.descs_t != t || w.descs_kmax != kmax) {
+    // the descriptors only depend on (t, kmax): uploaded once per work set
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(d_descs, bwd.data(), sizeof(PassDesc) * (kMaxBuckets + 1),
                                     cudaMemcpyHostToDevice, st));
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(d_descs + (kMaxBuckets + 1), fwd.data(), sizeof(PassDesc) * (kMaxBuckets + 1),
@@ -296,7 +301,6 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
     BCHFFT_CUDA_TRY(cudaStreamSynchronize(st));          // bwd is a stack object
     w.descs_t = t;
     w.descs_kmax = kmax;
-    w.descs_at = d_descs;
   }
   BCHFFT_CUDA_TRY(cudaMemsetAsync(counts, 0, (kMaxBuckets + 1) * 4, st));
   BCHFFT_RUN(k_bucket, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, (const int32_t *)s.flag,
@@ -360,7 +364,8 @@ static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words
   chunk = (chunk / 32) * 32;
   if (chunk < 32) chunk = 32;
   if (chunk > batch) chunk = batch;
-  if (chunk > (size_t)65535 * 32) chunk = (size_t)65535 * 32;
+  // gridDim.y limits: k_syndrome launches one row per slab, k_locate one per virtual slab (slabs + kmax)
+  if (chunk > (size_t)(65535 - kMaxBuckets) * 32) chunk = (size_t)(65535 - kMaxBuckets) * 32;
   int rc = w.scratch.reserve(scratch_bytes(c, chunk, pos_stride, M));
   if (rc) return rc;
   for (size_t i0 = 0; i0 < batch; i0 += chunk) {
@@ -383,6 +388,16 @@ static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words
                   (const uint32_t *)s.count, (const uint32_t *)s.positions, s.pos_stride,
                   d_ok ? d_ok + i0 : (uint8_t *)nullptr, d_corrected ? d_corrected + i0 : (uint32_t *)nullptr);
   }
+  return BCHFFT_OK;
+}
+
+// cudaMalloc + checked synchronous upload of a host vector (tables built once per code)
+template <class T>
+static int upload_table(const std::vector<T> &v, T **out)
+{
+  *out = nullptr;
+  BCHFFT_CUDA_TRY(cudaMalloc((void **)out, v.size() * sizeof(T) + 16));
+  BCHFFT_CUDA_TRY(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   return BCHFFT_OK;
 }
 
@@ -427,8 +442,11 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
     return BCHFFT_ERR_ARG;
   }
   *out = nullptr;
-  if (distance < 3 || !(distance & 1u) || length < 2 || length > f->n || distance >= length) {
-    set_error("bchfft_code_create: need odd distance >= 3 and distance < length <= 2^m");
+  // any designed distance the reference accepts (bch.c:37: d < length): t = (d-1)/2 errors are
+  // corrected, Berlekamp-Massey runs d-1 iterations on S_1 .. S_(d-1) (bch.c:340), so an even d
+  // needs one more odd syndrome class than an odd one: nodd = d/2
+  if (distance < 3 || length < 2 || length > f->n || distance >= length) {
+    set_error("bchfft_code_create: need 3 <= distance < length <= 2^m");
     return BCHFFT_ERR_ARG;
   }
   BCHFFT_CUDA_TRY(cudaSetDevice(f->device));
@@ -439,7 +457,7 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
   c->length = length;
   c->gen_degree = gen_poly_degree;
   c->wpc = (length - 1u) / 64u + 1u;
-  c->nodd = c->t;
+  c->nodd = distance / 2u;
   {
     // method rule of bch_eval_syndrome (bch.c:240-254), float arithmetic as in the reference
     const float threshold = 0.5f * f->m * f->m;
@@ -500,17 +518,14 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
       par &= 1u;
     }
   }
-  cudaError_t e0 = cudaMalloc((void **)&c->d_vbits, vbits.size() * 4 + 16);
-  if (e0 == cudaSuccess) cudaMemcpy(c->d_vbits, vbits.data(), vbits.size() * 4, cudaMemcpyHostToDevice);
-  cudaError_t e1 = (e0 != cudaSuccess) ? e0 : cudaMalloc((void **)&c->d_taps, taps.size() * 4 + 16);
-  cudaError_t e2 = cudaMalloc((void **)&c->d_fold, fold.size() * 4 + 16);
-  if (e1 != cudaSuccess || e2 != cudaSuccess) {
-    set_error("bchfft_code_create: cudaMalloc failed");
-    bchfft_code_destroy(c);
-    return BCHFFT_ERR_CUDA;
+  {
+    int urc;
+    if ((urc = upload_table(vbits, &c->d_vbits)) || (urc = upload_table(taps, &c->d_taps)) ||
+        (urc = upload_table(fold, &c->d_fold))) {
+      bchfft_code_destroy(c);
+      return urc;
+    }
   }
-  cudaMemcpy(c->d_taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice);
-  cudaMemcpy(c->d_fold, fold.data(), fold.size() * 4, cudaMemcpyHostToDevice);
   // universal-LFSR syndromes: every class j must permute the positions (gcd(j, order) = 1), the
   // whole codeword must fit shared memory, and no codeword bit may sit at position >= order
   {
@@ -586,53 +601,80 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
           }
         }
       }
-      cudaError_t p0 = cudaMalloc((void **)&c->d_jinv, jinv.size() * 4 + 16);
-      cudaError_t p1 = cudaMalloc((void **)&c->d_start, start.size() * 4 + 16);
-      cudaError_t p2 = cudaMalloc((void **)&c->d_foldp, foldp.size() * 4 + 16);
-      cudaError_t p3 = cudaMalloc((void **)&c->d_lcs, lcs.size() * 4 + 16);
-      if (p0 != cudaSuccess || p1 != cudaSuccess || p2 != cudaSuccess || p3 != cudaSuccess) {
-        set_error("bchfft_code_create: cudaMalloc failed");
+      int urc;
+      if ((urc = upload_table(jinv, &c->d_jinv)) || (urc = upload_table(start, &c->d_start)) ||
+          (urc = upload_table(foldp, &c->d_foldp)) || (urc = upload_table(lcs, &c->d_lcs))) {
         bchfft_code_destroy(c);
-        return BCHFFT_ERR_CUDA;
+        return urc;
       }
-      cudaMemcpy(c->d_jinv, jinv.data(), jinv.size() * 4, cudaMemcpyHostToDevice);
-      cudaMemcpy(c->d_start, start.data(), start.size() * 4, cudaMemcpyHostToDevice);
-      cudaMemcpy(c->d_foldp, foldp.data(), foldp.size() * 4, cudaMemcpyHostToDevice);
-      cudaMemcpy(c->d_lcs, lcs.data(), lcs.size() * 4, cudaMemcpyHostToDevice);
       c->syn_p = 1u;
     }
   }
-  // encoder table (needs the generator polynomial; degree 8 .. 2048)
-  if (packed_gen_poly && gen_poly_degree >= 8u && gen_poly_degree <= 2048u && gen_poly_degree < length) {
+  // encoder tables (need the generator polynomial)
+  if (packed_gen_poly && gen_poly_degree >= 8u && gen_poly_degree < length) {
     const uint32_t dg = gen_poly_degree, gw = (dg >> 6) + 1u;
+    const char *wenv = getenv("BCHFFT_ENC_WIDE");   // test hook: force the warp-per-codeword encoder
+    const bool wide = dg > 2048u || (wenv && atoi(wenv) != 0 && dg >= 64u);
+    std::vector<uint64_t> table, r(gw + 1u);
     uint32_t nw = 1;
-    while (nw * 64u < dg) nw *= 2u;
-    std::vector<uint64_t> table((size_t)256 * nw, 0ull), r(gw + 1u);
-    for (uint32_t v = 0; v < 256u; v++) {
-      // r = v(X) X^dg mod g: feed the 8 bits of v (highest first) through the division by g
-      std::fill(r.begin(), r.end(), 0ull);
-      for (int bit = 7; bit >= 0; bit--) {
-        const uint32_t fb = (uint32_t)((r[(dg - 1u) >> 6] >> ((dg - 1u) & 63u)) & 1ull) ^ ((v >> bit) & 1u);
-        uint64_t carry = 0;
-        for (uint32_t k = 0; k < gw; k++) {
-          const uint64_t nc = r[k] >> 63;
-          r[k] = (r[k] << 1) | carry;
-          carry = nc;
-        }
-        r[dg >> 6] &= ~(1ull << (dg & 63u));                   // drop the bit shifted out of degree dg-1
-        if (fb)
-          for (uint32_t k = 0; k < gw; k++) r[k] ^= packed_gen_poly[k];
-        r[dg >> 6] &= (dg & 63u) ? ((1ull << (dg & 63u)) - 1ull) : 0ull;   // g's leading coefficient
+    // r <- r X mod g (r has degree < dg)
+    auto times_x = [&]() {
+      uint64_t carry = 0;
+      for (uint32_t k = 0; k < gw; k++) {
+        const uint64_t nc = r[k] >> 63;
+        r[k] = (r[k] << 1) | carry;
+        carry = nc;
       }
-      for (uint32_t k = 0; k < nw && k < gw; k++) table[(size_t)v * nw + k] = r[k];
+      if ((r[dg >> 6] >> (dg & 63u)) & 1ull)
+        for (uint32_t k = 0; k < gw; k++) r[k] ^= packed_gen_poly[k];
+    };
+    if (wide) {
+      // rows[k] = X^(dg+k) mod g: row 0 is g without its leading term
+      table.assign((size_t)64 * gw, 0ull);
+      for (uint32_t k = 0; k < gw; k++) r[k] = packed_gen_poly[k];
+      r[dg >> 6] &= ~(1ull << (dg & 63u));
+      for (uint32_t row = 0; row < 64u; row++) {
+        for (uint32_t k = 0; k < gw; k++) table[(size_t)row * gw + k] = r[k];
+        times_x();
+      }
+    } else {
+      while (nw * 64u < dg) nw *= 2u;
+      table.assign((size_t)256 * nw, 0ull);
+      for (uint32_t v = 0; v < 256u; v++) {
+        // r = v(X) X^dg mod g: feed the 8 bits of v (highest first) through the division by g
+        std::fill(r.begin(), r.end(), 0ull);
+        for (int bit = 7; bit >= 0; bit--) {
+          const uint32_t fb = (uint32_t)((r[(dg - 1u) >> 6] >> ((dg - 1u) & 63u)) & 1ull) ^ ((v >> bit) & 1u);
+          uint64_t carry = 0;
+          for (uint32_t k = 0; k < gw; k++) {
+            const uint64_t nc = r[k] >> 63;
+            r[k] = (r[k] << 1) | carry;
+            carry = nc;
+          }
+          r[dg >> 6] &= ~(1ull << (dg & 63u));                   // drop the bit shifted out of degree dg-1
+          if (fb)
+            for (uint32_t k = 0; k < gw; k++) r[k] ^= packed_gen_poly[k];
+          r[dg >> 6] &= (dg & 63u) ? ((1ull << (dg & 63u)) - 1ull) : 0ull;   // g's leading coefficient
+        }
+        for (uint32_t k = 0; k < nw && k < gw; k++) table[(size_t)v * nw + k] = r[k];
+      }
     }
-    if (cudaMalloc((void **)&c->d_enc_table, table.size() * 8 + 16) != cudaSuccess) {
-      set_error("bchfft_code_create: cudaMalloc failed");
+    int urc = upload_table(table, &c->d_enc_table);
+    if (urc) {
+      bchfft_code_destroy(c);
+      return urc;
+    }
+    c->enc_nw = wide ? gw : nw;
+    c->enc_wide = wide ? 1u : 0u;
+  }
+  // every table is in place before the first kernel on a non-blocking stream can read it
+  {
+    const cudaError_t se = cudaDeviceSynchronize();
+    if (se != cudaSuccess) {
+      set_error("bchfft_code_create: table upload failed: %s", cudaGetErrorString(se));
       bchfft_code_destroy(c);
       return BCHFFT_ERR_CUDA;
     }
-    cudaMemcpy(c->d_enc_table, table.data(), table.size() * 8, cudaMemcpyHostToDevice);
-    c->enc_nw = nw;
   }
   *out = c;
   return BCHFFT_OK;
@@ -659,6 +701,7 @@ extern "C" void bchfft_code_destroy(bchfft_code *c)
     w.corr.release();
     w.fft_ws.release();
     w.fft_io.release();
+    w.descs.release();
     if (w.stream) cudaStreamDestroy(w.stream);
   }
   delete c;
@@ -746,6 +789,18 @@ extern "C" int bchfft_bch_decode_host(bchfft_code *c, uint64_t *words, size_t ba
 static int encode_launch(bchfft_code *c, const uint64_t *d_data, uint32_t dwords, uint32_t data_bits,
                          uint64_t *d_cw, size_t batch, cudaStream_t st)
 {
+  if (c->enc_wide) {
+#ifdef BCHFFT_EMU
+    const unsigned nt = 32;
+#else
+    const unsigned nt = 256;
+#endif
+    const size_t smem_w = (size_t)(nt / 32) * 2u * c->enc_nw * 8;
+    BCHFFT_ENSURE_SMEM(k_encode_wide, c->f->device, smem_w);
+    BCHFFT_RUN(k_encode_wide, dim3((unsigned)((batch + nt / 32 - 1) / (nt / 32))), dim3(nt), smem_w, st, d_data, dwords,
+               data_bits, c->gen_degree, (const uint64_t *)c->d_enc_table, d_cw, c->wpc, (uint32_t)batch);
+    return BCHFFT_OK;
+  }
   const size_t smem = (size_t)256 * c->enc_nw * 8;
   const dim3 grid((unsigned)((batch + 127) / 128)), block(128);
 #define ENC(NW)                                                                                        \
@@ -771,7 +826,7 @@ static int encode_check(bchfft_code *c, const void *data, const void *cw, uint32
     return BCHFFT_ERR_ARG;
   }
   if (!c->enc_nw) {
-    set_error("%s: the code context has no encoder (generator polynomial missing, or its degree is outside 8..2048)", who);
+    set_error("%s: the code context has no encoder (generator polynomial missing, or its degree is below 8)", who);
     return BCHFFT_ERR_UNSUPPORTED;
   }
   if (data_bits > c->length - c->gen_degree) {   // bch.c:495

@@ -2,6 +2,7 @@
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <map>
 #include <string>
 #include <vector>
@@ -14,7 +15,7 @@
 namespace bchfft {
 
 void set_error(const char *fmt, ...);
-extern uint64_t g_launches;
+extern std::atomic<uint64_t> g_launches;
 
 #define BCHFFT_CUDA_TRY(expr)                                                              \
   do {                                                                                     \

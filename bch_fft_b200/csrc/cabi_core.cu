@@ -2,13 +2,14 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 
 #include "cabi_common.h"
 
 namespace bchfft {
 
 static thread_local char g_err[512] = "";
-uint64_t g_launches = 0;
+std::atomic<uint64_t> g_launches{0};
 
 void set_error(const char *fmt, ...)
 {
@@ -38,7 +39,10 @@ void DeviceBuffer::release()
 
 int ensure_smem(const void *kernel, int device, size_t bytes)
 {
+  // process-wide table: callers on different contexts / devices may run concurrently
+  static std::mutex mu;
   static std::map<std::pair<const void *, int>, size_t> high_water;
+  std::lock_guard<std::mutex> guard(mu);
   size_t &hw = high_water[std::make_pair(kernel, device)];
   if (bytes <= hw) return BCHFFT_OK;
 #ifdef BCHFFT_EMU
@@ -56,6 +60,8 @@ struct ProfRec {
   const char *name;
   cudaEvent_t a, b;
 };
+// (the profiling API is a single-threaded measurement tool: bench.py drives it from one thread with
+// no other caller active -- see bchfft_cuda.h)
 static bool g_prof = false;
 static std::vector<ProfRec> g_prof_recs;
 static cudaStream_t g_prof_stream = nullptr;
@@ -299,6 +305,14 @@ extern "C" int bchfft_field_create(int device, uint32_t m, const uint32_t *exp, 
   cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    bchfft_field_destroy(f);
+    return BCHFFT_ERR_CUDA;
+  }
+  // the uploads came from pageable memory on the legacy stream; kernels run on non-blocking streams
+  // that do not order against it: make sure every table has landed before the context is handed out
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("bchfft_field_create: table upload failed: %s", cudaGetErrorString(e));
     bchfft_field_destroy(f);
     return BCHFFT_ERR_CUDA;
   }

@@ -117,6 +117,11 @@ TbchCode bch_gen_code(uint32_t p_codeword_size, uint32_t p_minimum_distance)
   if (p_minimum_distance >= p_codeword_size || p_codeword_size > (1u << g_maxDegree)) return code;
   uint32_t m = 2;
   while ((1u << m) < p_codeword_size) m++;
+  /* Parameters the device decoder has no kernels for give the reference's failure value (no
+   * generator) here, instead of a code whose first decode call would have to abort: fields above
+   * GF(2^25) (the reference's own tables for m = 26..30 are not primitive) and
+   * designed distances below 3 (nothing to correct). */
+  if (m > BCHFFT_MAX_FIELD_DEGREE || p_minimum_distance < 3) return code;
   TfiniteField f = create_binary_finite_field(m);
   code = bch_build_polynomial(&f, p_minimum_distance);
   if (code.m_gen_poly_degree >= p_codeword_size) bch_free_code(&code);   /* no data bits left */

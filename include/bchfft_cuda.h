@@ -27,6 +27,10 @@ extern "C" {
 typedef struct bchfft_field bchfft_field; /* per (device, GF(2^m)) state: tables, constants, workspace */
 typedef struct bchfft_code bchfft_code;   /* per BCH code state on top of a field */
 
+/* largest field degree the kernels are compiled for (GF(2^2) .. GF(2^25): every field of the
+ * reference's table whose x is primitive, libbase/finite_field.c:9-18) */
+#define BCHFFT_MAX_FIELD_DEGREE 25
+
 #define BCHFFT_OK 0
 #define BCHFFT_ERR_CUDA (-1)     /* CUDA runtime error (no device, launch failure, ...) */
 #define BCHFFT_ERR_ARG (-2)      /* invalid argument */
@@ -102,7 +106,7 @@ int bchfft_bch_decode_dev(bchfft_code *c, uint64_t *d_words, size_t batch, uint8
  * data bit i at codeword bit i + deg(g), parity (data X^deg(g) mod g) in bits 0 .. deg(g)-1, the
  * rest zero.  BCHFFT_ERR_ARG when data_bits > length - deg(g) (where the reference returns 1);
  * BCHFFT_ERR_UNSUPPORTED when the code context was created without its generator polynomial or
- * deg(g) is outside 8..2048. */
+ * deg(g) < 8. */
 int bchfft_bch_encode_host(bchfft_code *c, const uint64_t *data, size_t data_words, uint32_t data_bits,
                            uint64_t *codewords, size_t batch);
 int bchfft_bch_encode_dev(bchfft_code *c, const uint64_t *d_data, size_t data_words, uint32_t data_bits,

@@ -135,17 +135,20 @@ class Port:
             raise ValueError("unknown factorisation")
         return out[: n - 1]
 
-    def code(self, length, t):
-        return PortCode(self, length, t)
+    def code(self, length, t, d=None):
+        return PortCode(self, length, t, d)
 
 
 class PortCode:
-    def __init__(self, port, length, t):
+    def __init__(self, port, length, t, d=None):
+        """d: designed distance when it is not 2t+1 (even distances: t = (d-1)//2)"""
         self.port, self.lib = port, port.lib
         self.c = _OrcCode()
-        if self.lib.orc_bch_gen(C.byref(self.c), length, 2 * t + 1):
+        d = 2 * t + 1 if d is None else d
+        t = (d - 1) // 2
+        if self.lib.orc_bch_gen(C.byref(self.c), length, d):
             raise ValueError("code could not be created")
-        self.length, self.t, self.d = length, t, 2 * t + 1
+        self.length, self.t, self.d = length, t, d
         self.m = self.c.f.m
         self.gen_degree = self.c.gen_degree
         self.words = (length - 1) // 64 + 1
@@ -305,17 +308,19 @@ class Ref:
             raise ValueError("unknown factorisation")
         return out[: n - 1]
 
-    def code(self, length, t):
-        return RefCode(self, length, t)
+    def code(self, length, t, d=None):
+        return RefCode(self, length, t, d)
 
 
 class RefCode:
-    def __init__(self, ref, length, t):
+    def __init__(self, ref, length, t, d=None):
         self.ref, self.lib = ref, ref.lib
-        self.c = self.lib.bch_gen_code(length, 2 * t + 1)
+        d = 2 * t + 1 if d is None else d
+        t = (d - 1) // 2
+        self.c = self.lib.bch_gen_code(length, d)
         if not self.c.m_packed_gen_poly:
             raise ValueError("code could not be created")
-        self.length, self.t, self.d = length, t, 2 * t + 1
+        self.length, self.t, self.d = length, t, d
         self.m = self.c.m_field.m
         self.gen_degree = self.c.m_gen_poly_degree
         self.words = (length - 1) // 64 + 1

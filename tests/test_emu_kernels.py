@@ -53,6 +53,18 @@ def test_emu_additive_fft_vs_oracle(emu_libs, port, m):
     cabi.bchfft_field_destroy(h)
 
 
+def test_emu_additive_fft_gf2_17_vs_reference(emu_libs, ref):
+    """a field above GF(2^16) with a single-depth Cantor chain (odd m): multi-pass schedule, 4-byte
+    elements, 20-word plane stride; full and truncated degree against the unmodified reference"""
+    _, host = emu_libs
+    m, n = 17, 1 << 17
+    f = host.create_binary_finite_field(m)
+    polys = synth.random_polys(m, 2, 77 + m)
+    for terms in (n - 1, 1000):
+        want, _ = ref.additive_fft_batch_mt(m, polys, terms, 2)
+        assert (f.additive_fft_batch(polys, terms) == want).all(), terms
+
+
 @pytest.mark.parametrize("rec", [r for r in GOLDEN["additive"] if r["m"] <= 13],
                          ids=lambda r: f"m{r['m']}-terms{r['num_terms']}")
 def test_emu_additive_fft_golden(emu_libs, port, rec):
@@ -206,6 +218,25 @@ def _encode_cases(host, port, n, t, rng):
         code.encode_batch(np.zeros((2, (k + 64) // 64 + 1), np.uint64), k + 1)     # bch.c:495
 
 
+@pytest.mark.parametrize("n,t", [(8191, 200), (1023, 10), (4000, 30)])
+def test_emu_encode_batch_wide(emu_libs, port, n, t):
+    """warp-per-codeword encoder (k_encode_wide): any generator degree >= 64 -- the (8191, 200) code
+    (deg g = 2444) takes it by default, BCHFFT_ENC_WIDE=1 forces it for smaller codes.  Run in a
+    subprocess because the code context (and its encoder choice) is cached per process."""
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from bch_fft_b200 import api\n"
+        "from oracle.pyoracle import Port\n"
+        "from tests.conftest import EMU_HOST\n"
+        "from tests.test_emu_kernels import _encode_cases\n"
+        f"_encode_cases(api.Host(EMU_HOST), Port(), {n}, {t}, np.random.default_rng({n + t}))\n"
+        "print('ok')\n")
+    env = dict(os.environ, BCHFFT_ENC_WIDE="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=ROOT)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]
+
+
 @pytest.mark.parametrize("n,t", [(255, 8), (8191, 16), (8191, 64), (5000, 12), (1023, 10)])
 def test_emu_encode_batch(emu_libs, port, n, t):
     _, host = emu_libs
@@ -296,7 +327,9 @@ def test_emu_edge_cases_and_errors(emu_libs, port):
     # code creation argument checks (bch.c:37: distance >= length is no code)
     c = C.c_void_p()
     assert cabi.bchfft_code_create(h, 255, 255, None, 0, C.byref(c)) < 0
-    assert cabi.bchfft_code_create(h, 4, 255, None, 0, C.byref(c)) < 0          # even distance
+    assert cabi.bchfft_code_create(h, 2, 255, None, 0, C.byref(c)) < 0          # nothing to correct
+    assert cabi.bchfft_code_create(h, 4, 255, None, 0, C.byref(c)) == 0         # even distances are codes (bch.c:37)
+    cabi.bchfft_code_destroy(c)
     pc = port.code(255, 8)
     assert cabi.bchfft_code_create(h, 17, 255, pc.gen.ctypes.data, pc.gen_degree, C.byref(c)) == 0
     words = np.zeros((1, pc.words), np.uint64)
@@ -527,3 +560,35 @@ def _wide_bm_case(cabi, host, port, n, t, B, seed):
 def test_emu_wide_berlekamp_massey(emu_libs, port):
     cabi, host = emu_libs
     _wide_bm_case(cabi, host, port, 8191, 64, 9, 640)
+
+
+@pytest.mark.parametrize("n,d", [(255, 10), (1023, 6), (600, 12), (8191, 4)])
+def test_emu_even_designed_distance(emu_libs, port, ref, n, d):
+    """the reference accepts any designed distance d < length (bch.c:37); an even d corrects
+    t = (d-1)/2 errors and runs d-1 Berlekamp-Massey iterations.  Stages and decode against the
+    restatement and the unmodified reference."""
+    cabi, host = emu_libs
+    t = (d - 1) // 2
+    code = host.bch_gen_code(n, d)
+    pc, rc = port.code(n, t, d=d), ref.code(n, t, d=d)
+    assert code.gen_degree == rc.gen_degree and (code.gen == rc.gen).all() and (pc.gen == rc.gen).all()
+    B = 40
+    words = _words_for(pc, n, t, B, np.random.default_rng(n + d))
+    ok, corr, out = code.decode_batch(words)
+    for chk in (pc, rc):
+        rok, rcorr, rw = chk.decode_batch(words)
+        assert (ok == rok).all() and (corr == rcorr).all() and (out == rw).all(), chk
+    for b in range(0, B, 3):
+        fl, syn = code.eval_syndrome(words[b])
+        rfl, rsyn, _ = rc.syndrome(words[b])
+        assert fl == rfl and (syn == rsyn).all()
+        L, elp = code.compute_elp(syn)
+        rL, relp = rc.elp(syn)
+        assert L == rL and (elp == relp).all()
+
+
+def test_emu_gen_code_rejects_what_the_device_cannot_decode(emu_libs):
+    _, host = emu_libs
+    for n, d in ((255, 2), (255, 1), ((1 << 26) - 1, 5)):
+        with pytest.raises(ValueError):
+            host.bch_gen_code(n, d)

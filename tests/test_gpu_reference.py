@@ -1,0 +1,254 @@
+"""Parity of the CUDA path against the UNMODIFIED reference (oracle/_ref/libref_oracle.so: the
+reference's own sources compiled by oracle/Makefile; it travels to the GPU box as a prebuilt file).
+test_gpu_parity.py compares with the C restatement; here the chain is one hop shorter -- CUDA output
+against the reference's output on the same inputs -- for every BASELINE configuration and for the
+parameter ranges the reference nominally supports (fields up to GF(2^25), the (1048575, t = 100)
+code of SURVEY appendix C).  Everything is bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from bch_fft_b200 import _lib, synth
+from tests.common import flip, fnv64
+
+pytestmark = pytest.mark.gpu
+
+
+def _cores():
+    import os
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def test_reference_library_is_loaded(gpu_libs, ref):
+    assert ref.mul(13, 3, 7) == 9
+    maps = open("/proc/self/maps").read()
+    assert "libref_oracle.so" in maps and "libbchfft_cuda.so" in maps
+
+
+# ---- additive FFT ----------------------------------------------------------------------------
+@pytest.mark.parametrize("m,B", [(13, 70), (16, 40), (17, 6), (18, 5), (19, 4), (20, 3), (21, 2)])
+def test_additive_fft_vs_reference(gpu_libs, ref, m, B):
+    """evaluate_polynomial_additive_FFT (additive_fft.c:13-21): full degree, truncated degrees and the
+    clobbered natural-order array, for every BASELINE field and the fields between and above them"""
+    _, host = gpu_libs
+    n = 1 << m
+    f = host.create_binary_finite_field(m)
+    polys = synth.random_polys(m, B, 0xA0 + m)
+    for terms in (n - 1, 1000 % n, n // 2, n // 2 - 1, 0, 1):
+        got = f.additive_fft_batch(polys, terms)
+        want, _ = ref.additive_fft_batch_mt(m, polys, terms, _cores())
+        assert (got == want).all(), (m, terms)
+    # single-call entry point: po_result and the clobbered p_poly
+    p = polys[0].copy()
+    res = f.evaluate_polynomial_additive_FFT(p, n - 1)
+    rres, rnat = ref.additive_fft(m, polys[0], n - 1)
+    assert (res == rres).all() and (p == rnat).all()
+
+
+def _eval_points(exp, log, poly, idx):
+    """P(x^i) for i in idx by direct summation in the log domain (numpy, independent of any FFT)"""
+    order = len(exp) - 1
+    k = np.nonzero(poly)[0].astype(np.uint64)
+    lc = log[poly[k]].astype(np.uint64)
+    out = []
+    for i in idx:
+        e = (lc + (k * np.uint64(i)) % np.uint64(order)) % np.uint64(order)
+        out.append(int(np.bitwise_xor.reduce(exp[e.astype(np.int64)])))
+    return np.array(out, np.uint32)
+
+
+@pytest.mark.parametrize("m", [22, 24, 25])
+def test_additive_fft_large_fields(gpu_libs, ref, m):
+    """GF(2^22) .. GF(2^25), the top of the reference's field table (finite_field.c:9-18): truncated
+    evaluation against the reference (its low-degree shortcut keeps the CPU time in seconds), full
+    degree against direct evaluation at sampled points with the reference's own exp / log tables"""
+    _, host = gpu_libs
+    n = 1 << m
+    f = host.create_binary_finite_field(m)
+    rexp, rlog = ref.tables(m)
+    assert (f.exp == rexp).all() and (f.log == rlog).all()
+    polys = synth.random_polys(m, 2, 0xB0 + m)
+    got = f.additive_fft_batch(polys, 300)
+    want, _ = ref.additive_fft_batch_mt(m, polys, 300, 2)
+    assert (got == want).all()
+    got = f.additive_fft_batch(polys, n - 1)
+    idx = [0, 1, 2, n - 2, n // 3, 12345678 % (n - 1), (1 << (m - 1)) + 5]
+    for b in range(2):
+        assert (got[b, idx] == _eval_points(rexp, rlog, polys[b], idx)).all(), (m, b)
+    # linearity: FFT(a ^ b) = FFT(a) ^ FFT(b)
+    mix = (polys[0] ^ polys[1])[None, :].copy()
+    assert (f.additive_fft_batch(mix, n - 1)[0] == (got[0] ^ got[1])).all()
+
+
+def test_additive_fft_gf2_20_full_batch_vs_reference(gpu_libs, ref):
+    """BASELINE configs[3]: 256 polynomials over GF(2^20), 1 GiB of coefficients; 32 of
+    them (every 8th, plus neighbours of the slab boundaries) against the reference on all host cores,
+    the demo input's Appendix C fingerprint, and additive == multiplicative on the device"""
+    cabi, host = gpu_libs
+    m, n, B = 20, 1 << 20, 256
+    f = host.create_binary_finite_field(m)
+    polys = synth.random_polys(m, B, 0xC4)
+    polys[255] = synth.demo_poly(m)
+    got = f.additive_fft_batch(polys, n - 1)
+    assert fnv64(got[255]) == 0x43310189501ffec7
+    pick = sorted(set(range(0, B, 8)) | {31, 32, 33, 223, 224, 254})[:40]
+    want, _ = ref.additive_fft_batch_mt(m, polys[pick], n - 1, _cores())
+    assert (got[pick] == want).all()
+    mult = f.multiplicative_fft_batch(polys[:33], n - 1)
+    assert (mult == got[:33]).all()
+
+
+def test_additive_fft_gf2_16_full_batch_vs_reference(gpu_libs, ref):
+    """BASELINE configs[0] batched: 4096 polynomials over GF(2^16); 128 of them against
+    the reference, the demo input's fingerprint"""
+    _, host = gpu_libs
+    m, n, B = 16, 1 << 16, 4096
+    f = host.create_binary_finite_field(m)
+    polys = synth.random_polys(m, B, 0xC1)
+    polys[4095] = synth.demo_poly(m)
+    got = f.additive_fft_batch(polys, n - 1)
+    assert fnv64(got[4095]) == 0xda6143e12631d2df
+    pick = sorted(set(range(0, B, 33)) | {31, 32, 4064, 4094})
+    want, _ = ref.additive_fft_batch_mt(m, polys[pick], n - 1, _cores())
+    assert (got[pick] == want).all()
+
+
+# ---- multiplicative FFT ------------------------------------------------------------------------
+@pytest.mark.parametrize("m", [8, 9, 10, 11, 12, 14, 15, 16, 18, 20])
+def test_multiplicative_fft_vs_reference(gpu_libs, ref, m):
+    """multiplicative_FFT / evaluate_polynomial_multiplicative_FFT (multiplicative_fft.c:106-324) for
+    every factorisation of the reference's table with small prime factors, full and truncated"""
+    _, host = gpu_libs
+    n = 1 << m
+    f = host.create_binary_finite_field(m)
+    B = 36 if m <= 16 else 3
+    polys = synth.random_polys(m, B, 0xC5 + m)
+    full = f.multiplicative_fft_batch(polys, n - 1)
+    for b in (0, B - 1):
+        assert (full[b] == ref.mult_fft(m, polys[b, : n - 1])).all(), (m, b)
+    for nc in (1, 2, 15, 255, (n - 1) // 3, (n - 1) // 5 + 1, n - 2):
+        nc = min(nc, n - 1)
+        got = f.multiplicative_fft_batch(polys, nc)
+        for b in (0, B - 1):
+            assert (got[b] == ref.mult_eval(m, polys[b], nc)).all(), (m, nc, b)
+
+
+def test_multiplicative_fft_gf2_16_full_batch(gpu_libs, ref):
+    """BASELINE configs[4]: 4096 polynomials over GF(2^16) -- equal to the additive
+    path's po_result for the whole batch (fft/test.c:147 relation), 24 of them against the reference"""
+    _, host = gpu_libs
+    m, n, B = 16, 1 << 16, 4096
+    f = host.create_binary_finite_field(m)
+    polys = synth.random_polys(m, B, 0xC5)
+    mult = f.multiplicative_fft_batch(polys, n - 1)
+    add = f.additive_fft_batch(polys, n - 1)
+    assert (mult == add).all()
+    for b in list(range(0, B, 190)) + [31, 32, 4095]:
+        assert (mult[b] == ref.mult_fft(m, polys[b, : n - 1])).all(), b
+
+
+# ---- decode -------------------------------------------------------------------------------------
+def _words_for(rc, n, t, B, rng):
+    pool = [rc.encode(rng.integers(0, 2, n - rc.gen_degree, dtype=np.uint32)) for _ in range(4)]
+    words = np.zeros((B, rc.words), np.uint64)
+    for b in range(B):
+        w = pool[b % 4].copy()
+        ne = [0, 1, t, t // 2, t + 1, t + 2, t + 3][b % 7] if b < 28 else int(rng.integers(0, t + 1))
+        pos = rng.choice(n, min(ne, n), replace=False)
+        if b % 5 == 0 and ne:
+            pos[0] = 0                                # bit-0 quirk (bch.c:479-488)
+        for p in set(int(x) for x in pos):
+            flip(w, p)
+        words[b] = w
+    return words
+
+
+@pytest.mark.parametrize("n,t,B", [(8191, 16, 64), (8191, 64, 48), (8191, 200, 40), (65535, 100, 40),
+                                   (65535, 1000, 30), (1048575, 100, 34), (131071, 20, 34),
+                                   (262143, 10, 33)])
+def test_decode_stages_vs_reference(gpu_libs, ref, n, t, B):
+    """bch_eval_syndrome -> bch_compute_elp -> bch_locate_errors -> bch_decode (bch.c:228-562) on every
+    BASELINE code and on fields above GF(2^16) -- (1048575, 100) is the appendix C code over GF(2^20),
+    which runs k_syndrome<20>, k_bm<20>, k_locate<20> -- word by word against the reference"""
+    _, host = gpu_libs
+    code = host.bch_gen_code(n, 2 * t + 1)
+    rc = ref.code(n, t)
+    assert code.gen_degree == rc.gen_degree and (code.gen == rc.gen).all()
+    if (n, t) == (1048575, 100):
+        assert f"{fnv64(code.gen):016x}" == "38dc62bb051634f8"
+    words = _words_for(rc, n, t, B, np.random.default_rng(n * 3 + t))
+    ok, corr, out = code.decode_batch(words)
+    rok, rcorr, rout = rc.decode_batch(words)
+    assert (ok == rok).all() and (corr == rcorr).all() and (out == rout).all()
+    for b in list(range(0, 14)) + [B - 1]:
+        fl, syn = code.eval_syndrome(words[b])
+        rfl, rsyn, _ = rc.syndrome(words[b])
+        assert fl == rfl and (syn == rsyn).all(), b
+        L, elp = code.compute_elp(syn)
+        rL, relp = rc.elp(syn)
+        assert L == rL and (elp == relp).all(), b
+        if L <= t:
+            pos = code.locate_errors(elp, L)
+            assert (pos == rc.locate(relp, rL)).all(), b
+        o, c, w = code.decode(words[b])
+        assert (o, c) == (int(rok[b]), int(rcorr[b])) and (w == rout[b]).all(), b
+
+
+@pytest.mark.parametrize("n,d", [(8191, 34), (65535, 12)])
+def test_even_designed_distance_vs_reference(gpu_libs, ref, n, d):
+    """any designed distance the reference accepts (bch.c:37): even d = 2t+2"""
+    _, host = gpu_libs
+    t = (d - 1) // 2
+    code = host.bch_gen_code(n, d)
+    rc = ref.code(n, t, d=d)
+    assert (code.gen == rc.gen).all()
+    words = _words_for(rc, n, t, 60, np.random.default_rng(n + d))
+    ok, corr, out = code.decode_batch(words)
+    rok, rcorr, rout = rc.decode_batch(words)
+    assert (ok == rok).all() and (corr == rcorr).all() and (out == rout).all()
+
+
+@pytest.mark.parametrize("t,B", [(16, 40000), (64, 20000), (200, 12000)])
+def test_batched_decode_vs_reference_at_scale(gpu_libs, ref, t, B):
+    """BASELINE configs[2], all three codes of the survey: (8191, t) for t = 16, 64, 200
+    -- t >= 32 runs the general root-search kernel, t = 200 the reference's FFT paths -- with the
+    bench's error mix (0..t errors, 1 % beyond capacity, bit 0 included), every word compared with the
+    reference run on all host cores"""
+    _, host = gpu_libs
+    n = 8191
+    code = host.bch_gen_code(n, 2 * t + 1)
+    rc = ref.code(n, t)
+    bits = (synth.splitmix64(0xC3, 64 * code.data_bits) & np.uint64(1)).astype(np.uint32)
+    pool = np.stack([rc.encode(b) for b in bits.reshape(64, -1)])
+    words, nerr = synth.corrupt_codewords(pool, n, t, B, 0xC3 + t, beyond_fraction=0.01)
+    ok, corr, out = code.decode_batch(words)
+    rok, rcorr, rout, _ = rc.decode_batch_mt(words, _cores())
+    assert (ok == rok).all() and (corr == rcorr).all() and (out == rout).all()
+    assert 0.97 < ok.mean() < 1.0 and corr.max() >= t
+
+
+@pytest.mark.parametrize("n,t", [(8191, 200), (65535, 1000), (8191, 16)])
+def test_encode_batch_vs_reference(gpu_libs, ref, n, t):
+    """bch_encode (bch.c:492-506) for generator degrees on both sides of 2048: (8191, 200) has
+    deg g = 2444 and (65535, 1000) deg g = 15360 (warp-per-codeword kernel), (8191, 16) 208"""
+    _, host = gpu_libs
+    code = host.bch_gen_code(n, 2 * t + 1)
+    rc = ref.code(n, t)
+    k = code.data_bits
+    rng = np.random.default_rng(n + t)
+    for nbits in (k, k - 1, 65, 1):
+        B = 70
+        bits = rng.integers(0, 2, (B, nbits), dtype=np.uint32)
+        bits[0] = 0
+        bits[1] = 1
+        packed = np.zeros((B, (nbits + 63) // 64), np.uint64)
+        for w in range(packed.shape[1]):
+            chunk = bits[:, 64 * w: 64 * w + 64].astype(np.uint64)
+            packed[:, w] = (chunk << np.arange(chunk.shape[1], dtype=np.uint64)).sum(axis=1, dtype=np.uint64)
+        out = code.encode_batch(packed, nbits)
+        for b in (0, 1, 2, 33, B - 1):
+            assert (out[b] == rc.encode(bits[b])).all(), (n, t, nbits, b)

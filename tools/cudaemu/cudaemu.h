@@ -128,7 +128,9 @@ static inline void __syncthreads()
   cudaemu::State &s = cudaemu::st();
   swapcontext(&s.cur->ctx, &s.sched);
 }
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
+// fibers are cooperative: a warp barrier yields like a block barrier (stronger than needed, fine for
+// kernels whose warps all reach the same number of barriers)
+static inline void __syncwarp(unsigned = 0xffffffffu) { __syncthreads(); }
 static inline void __threadfence() {}
 
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
@@ -137,6 +139,7 @@ template <class T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; r
 template <class T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline unsigned __brev(unsigned x)
 {
