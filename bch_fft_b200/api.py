@@ -341,6 +341,10 @@ class DeviceCode:
         _lib.check(self.l, self.l.bchfft_bch_decode_dev(self.h, d_words, batch, d_ok, d_corrected,
                                                         stream), "bchfft_bch_decode_dev")
 
+    def encode_dev(self, d_data, data_words, data_bits, d_codewords, batch, stream=None):
+        _lib.check(self.l, self.l.bchfft_bch_encode_dev(self.h, d_data, data_words, data_bits, d_codewords,
+                                                        batch, stream), "bchfft_bch_encode_dev")
+
     def decode_host(self, words):
         w = np.ascontiguousarray(words, np.uint64).reshape(-1, self.code.words).copy()
         B = w.shape[0]

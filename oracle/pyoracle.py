@@ -245,7 +245,22 @@ class Ref:
         L.ref_additive_fft_batch_mt.restype = C.c_double
         L.ref_additive_fft_batch_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                                 C.c_size_t, C.c_int]
+        L.ref_multiplicative_fft_batch_mt.restype = C.c_double
+        L.ref_multiplicative_fft_batch_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        L.ref_bch_encode_batch_mt.restype = C.c_double
+        L.ref_bch_encode_batch_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p,
+                                              C.c_size_t, C.c_int]
         self._fields = {}
+
+    def multiplicative_fft_batch_mt(self, m, polys, nthreads):
+        """multi-threaded batch through the reference's multiplicative_FFT (in place on a copy);
+        returns (evals[B, n-1], wall seconds)"""
+        n = 1 << m
+        p = np.ascontiguousarray(polys, np.uint32).copy().reshape(-1, n)
+        dt = self.lib.ref_multiplicative_fft_batch_mt(C.byref(self.field(m)), p.ctypes.data, p.shape[0], nthreads)
+        if dt < 0:
+            raise ValueError("unknown factorisation")
+        return p[:, : n - 1], dt
 
     def additive_fft_batch_mt(self, m, polys, num_terms, nthreads):
         """multi-threaded batch through the reference's evaluate_polynomial_additive_FFT;
@@ -396,3 +411,12 @@ class RefCode:
         for i in range(w.shape[0]):
             ok[i], corr[i], w[i] = self._decode_one(w[i])
         return ok, corr, w
+
+    def encode_batch_mt(self, packed_data, data_bits, nthreads):
+        """multi-threaded batch through the reference's bch_encode from packed data bits
+        ([B, data_words] uint64); returns (codewords [B, W], wall seconds)"""
+        d = np.ascontiguousarray(packed_data, np.uint64)
+        out = np.zeros((d.shape[0], self.words), np.uint64)
+        dt = self.lib.ref_bch_encode_batch_mt(C.byref(self.c), d.ctypes.data, d.shape[1], data_bits,
+                                              out.ctypes.data, d.shape[0], nthreads)
+        return out, dt
