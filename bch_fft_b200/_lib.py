@@ -20,6 +20,7 @@ _u32 = C.c_uint32
 
 _SIGNATURES = {
     "bchfft_last_error": (C.c_char_p, []),
+    "bchfft_set_last_error": (None, [C.c_char_p]),
     "bchfft_device_count": (C.c_int, []),
     "bchfft_is_emulated": (C.c_int, []),
     "bchfft_field_create": (C.c_int, [C.c_int, _u32, _vp, _vp, C.POINTER(_vp)]),

@@ -105,6 +105,8 @@ using namespace bchfft;
 
 extern "C" const char *bchfft_last_error(void) { return g_err; }
 
+extern "C" void bchfft_set_last_error(const char *text) { set_error("%s", text ? text : ""); }
+
 extern "C" int bchfft_is_emulated(void)
 {
 #ifdef BCHFFT_EMU

@@ -198,11 +198,13 @@ void bch_free_buffers(TbchCodeBuffers* p_buffer)
 
 /* ---- decoding (GPU) ----------------------------------------------------------------------- */
 
+/* single-item calls run on the first device of the set; returns with the slot lock held */
 static bchfft_code* code_context(TbchCode* p_code, const char* who)
 {
   int status = 0;
-  bchfft_code* ctx = bchfft_host_code(p_code, &status);
-  if (!ctx) { bchfft_host_unlock(); bchfft_host_die(who, status); }
+  bchfft_host_lock_slot(0);
+  bchfft_code* ctx = bchfft_host_code(p_code, 0, &status);
+  if (!ctx) { bchfft_host_unlock_slot(0); bchfft_host_die(who, status); }
   return ctx;
 }
 
@@ -210,11 +212,10 @@ static bchfft_code* code_context(TbchCode* p_code, const char* who)
 int32_t bch_eval_syndrome(TbchCode* p_code, TbchCodeBuffers* p_buffer, unsigned long* p_packed_syndrome)
 {
   int32_t flag = 0;
-  bchfft_host_lock();
   bchfft_code* ctx = code_context(p_code, "bch_eval_syndrome");
   const int status = bchfft_bch_syndrome_host(ctx, (const uint64_t*) p_packed_syndrome, 1,
                                               p_buffer->m_syndrome, &flag);
-  bchfft_host_unlock();
+  bchfft_host_unlock_slot(0);
   if (status) bchfft_host_die("bch_eval_syndrome", status);
   return flag;
 }
@@ -223,10 +224,9 @@ int32_t bch_eval_syndrome(TbchCode* p_code, TbchCodeBuffers* p_buffer, unsigned 
 uint32_t bch_compute_elp(TbchCode* p_code, TbchCodeBuffers* p_buffer)
 {
   uint32_t L = 0;
-  bchfft_host_lock();
   bchfft_code* ctx = code_context(p_code, "bch_compute_elp");
   const int status = bchfft_bch_elp_host(ctx, p_buffer->m_syndrome, 1, p_buffer->m_C_elp, &L);
-  bchfft_host_unlock();
+  bchfft_host_unlock_slot(0);
   if (status) bchfft_host_die("bch_compute_elp", status);
   return L;
 }
@@ -235,11 +235,10 @@ uint32_t bch_compute_elp(TbchCode* p_code, TbchCodeBuffers* p_buffer)
 uint32_t bch_locate_errors(TbchCode* p_code, TbchCodeBuffers* p_buffer, uint32_t p_elp_degree)
 {
   uint32_t count = 0;
-  bchfft_host_lock();
   bchfft_code* ctx = code_context(p_code, "bch_locate_errors");
   const int status = bchfft_bch_locate_host(ctx, p_buffer->m_C_elp, &p_elp_degree, 1,
                                             p_buffer->m_error, &count);
-  bchfft_host_unlock();
+  bchfft_host_unlock_slot(0);
   if (status) bchfft_host_die("bch_locate_errors", status);
   return count;
 }
@@ -251,36 +250,76 @@ uint32_t bch_decode(TbchCode* p_code, unsigned long* pio_packed_data, TbchCodeBu
   (void) p_buffer;   /* scratch lives on the device */
   unsigned char ok = 0;
   uint32_t corrected = 0;
-  bchfft_host_lock();
   bchfft_code* ctx = code_context(p_code, "bch_decode");
   const int status = bchfft_bch_decode_host(ctx, (uint64_t*) pio_packed_data, 1, &ok, &corrected);
-  bchfft_host_unlock();
+  bchfft_host_unlock_slot(0);
   if (status) bchfft_host_die("bch_decode", status);
   if (po_corrected) *po_corrected = corrected;
   return ok;
 }
 
+/* ---- batch entry points: one contiguous range of the caller's arrays per device ------------- */
+typedef struct
+{
+  TbchCode* code;
+  unsigned long* words;
+  unsigned char* ok;
+  uint32_t* corrected;
+  size_t wpc;
+} decode_batch_args;
+
+static int decode_shard(int slot, size_t lo, size_t hi, void* p)
+{
+  decode_batch_args* a = (decode_batch_args*) p;
+  int status = 0;
+  bchfft_host_lock_slot(slot);
+  bchfft_code* ctx = bchfft_host_code(a->code, slot, &status);
+  if (ctx)
+    status = bchfft_bch_decode_host(ctx, (uint64_t*) (a->words + lo * a->wpc), hi - lo,
+                                    a->ok ? a->ok + lo : NULL, a->corrected ? a->corrected + lo : NULL);
+  bchfft_host_unlock_slot(slot);
+  return status;
+}
+
 int bch_decode_batch(TbchCode* p_code, unsigned long* pio_words, size_t p_count,
                      unsigned char* po_ok, uint32_t* po_corrected)
 {
+  decode_batch_args a = {p_code, pio_words, po_ok, po_corrected,
+                         degree_to_packed_size(p_code->m_length - 1)};
+  /* a device is worth a thread of its own from about 16 MiB of codewords on */
+  size_t min_per = ((size_t) 16 << 20) / (a.wpc * sizeof(unsigned long));
+  if (min_per < 1024) min_per = 1024;
+  return bchfft_host_run_sharded(p_count, min_per, decode_shard, &a);
+}
+
+typedef struct
+{
+  TbchCode* code;
+  unsigned long* codewords;
+  const unsigned long* data;
+  size_t data_words, wpc;
+  uint32_t data_bits;
+} encode_batch_args;
+
+static int encode_shard(int slot, size_t lo, size_t hi, void* p)
+{
+  encode_batch_args* a = (encode_batch_args*) p;
   int status = 0;
-  bchfft_host_lock();
-  bchfft_code* ctx = bchfft_host_code(p_code, &status);
+  bchfft_host_lock_slot(slot);
+  bchfft_code* ctx = bchfft_host_code(a->code, slot, &status);
   if (ctx)
-    status = bchfft_bch_decode_host(ctx, (uint64_t*) pio_words, p_count, po_ok, po_corrected);
-  bchfft_host_unlock();
+    status = bchfft_bch_encode_host(ctx, (const uint64_t*) (a->data + lo * a->data_words), a->data_words,
+                                    a->data_bits, (uint64_t*) (a->codewords + lo * a->wpc), hi - lo);
+  bchfft_host_unlock_slot(slot);
   return status;
 }
 
 int bch_encode_batch(TbchCode* p_code, unsigned long* po_codewords, const unsigned long* p_data,
                      size_t p_data_words, uint32_t p_data_bits, size_t p_count)
 {
-  int status = 0;
-  bchfft_host_lock();
-  bchfft_code* ctx = bchfft_host_code(p_code, &status);
-  if (ctx)
-    status = bchfft_bch_encode_host(ctx, (const uint64_t*) p_data, p_data_words, p_data_bits,
-                                    (uint64_t*) po_codewords, p_count);
-  bchfft_host_unlock();
-  return status;
+  encode_batch_args a = {p_code, po_codewords, p_data, p_data_words,
+                         degree_to_packed_size(p_code->m_length - 1), p_data_bits};
+  size_t min_per = ((size_t) 16 << 20) / (a.wpc * sizeof(unsigned long));
+  if (min_per < 1024) min_per = 1024;
+  return bchfft_host_run_sharded(p_count, min_per, encode_shard, &a);
 }

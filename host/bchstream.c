@@ -170,6 +170,9 @@ int main(int argc, char** argv)
           "%.3f s wall (%.3e codewords/s), %.3f s inside bch_decode_batch (%.3e codewords/s)\n",
           total, code.m_length, t, total_ok, total_bits, wall, wall > 0 ? total / wall : 0.,
           busy, busy > 0 ? total / busy : 0.);
+  if (rc)
+    return 1;   /* the reader was not joined and may still be inside fread() into a batch buffer:
+                   leave the buffers alone, the process ends here */
   for (int i = 0; i < NBUF; i++)
   {
     bchfft_pinned_free(batch[i].words);
@@ -177,5 +180,5 @@ int main(int argc, char** argv)
     bchfft_pinned_free(batch[i].corrected);
   }
   bch_free_code(&code);
-  return rc || io_error;
+  return io_error;
 }

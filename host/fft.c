@@ -14,17 +14,45 @@
 
 /* ---- additive FFT ----------------------------------------------------------------------- */
 
+typedef struct
+{
+  TfiniteField* f;
+  const uint32_t* polys;
+  uint32_t* results;
+  uint32_t* natural;
+  uint32_t num_terms;
+  int mult;              /* 1: multiplicative transform, num_terms = number of coefficients */
+} fft_batch_args;
+
+static int fft_shard(int slot, size_t lo, size_t hi, void* p)
+{
+  fft_batch_args* a = (fft_batch_args*) p;
+  const size_t n = a->f->n;
+  int status = 0;
+  bchfft_host_lock_slot(slot);
+  bchfft_field* ctx = bchfft_host_field(a->f, slot, &status);
+  if (ctx && a->mult)
+    status = bchfft_multiplicative_fft_host(ctx, a->polys + lo * n, n, a->results + lo * n, n, a->num_terms, hi - lo);
+  else if (ctx)
+    status = bchfft_additive_fft_host(ctx, a->polys + lo * n, n, a->results ? a->results + lo * n : NULL, n,
+                                      a->natural ? a->natural + lo * n : NULL, n, a->num_terms, hi - lo);
+  bchfft_host_unlock_slot(slot);
+  return status;
+}
+
+/* one contiguous range of polynomials per device (a device is worth its own thread from about 32 MiB
+ * of coefficients on); single transforms run on the first device */
+static size_t fft_min_per_device(const TfiniteField* p_f)
+{
+  size_t min_per = ((size_t) 32 << 20) / ((size_t) p_f->n * sizeof(uint32_t));
+  return min_per < 32 ? 32 : min_per;
+}
+
 static int additive_run(TfiniteField* p_f, const uint32_t* polys, uint32_t* results, uint32_t* natural,
                         uint32_t num_terms, size_t count)
 {
-  int status = 0;
-  bchfft_host_lock();
-  bchfft_field* ctx = bchfft_host_field(p_f, &status);
-  if (ctx)
-    status = bchfft_additive_fft_host(ctx, polys, p_f->n, results, p_f->n, natural, p_f->n,
-                                      num_terms, count);
-  bchfft_host_unlock();
-  return status;
+  fft_batch_args a = {p_f, polys, results, natural, num_terms, 0};
+  return bchfft_host_run_sharded(count, fft_min_per_device(p_f), fft_shard, &a);
 }
 
 /* replaces libfft/additive_fft.c:13-21 */
@@ -222,13 +250,8 @@ void multiplicative_FFT_step_chaining(TfiniteField* p_f, uint32_t* pio_data, uin
 static int multiplicative_run(TfiniteField* p_f, const uint32_t* polys, uint32_t* evals,
                               uint32_t num_coeffs, size_t count)
 {
-  int status = 0;
-  bchfft_host_lock();
-  bchfft_field* ctx = bchfft_host_field(p_f, &status);
-  if (ctx)
-    status = bchfft_multiplicative_fft_host(ctx, polys, p_f->n, evals, p_f->n, num_coeffs, count);
-  bchfft_host_unlock();
-  return status;
+  fft_batch_args a = {p_f, polys, evals, NULL, num_coeffs, 1};
+  return bchfft_host_run_sharded(count, fft_min_per_device(p_f), fft_shard, &a);
 }
 
 /* replaces libfft/multiplicative_fft.c:106-122 */

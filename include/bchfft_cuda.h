@@ -13,6 +13,12 @@
  * "_host" variants take host pointers and do the host<->device copies themselves on the
  * context's stream; "_dev" variants take device pointers (HBM-resident data) and only enqueue
  * work on the given stream.
+ *
+ * Threading: contexts that live on DIFFERENT devices may be used concurrently from different host
+ * threads (the host library drives one thread per GPU that way).  Calls on contexts of the SAME device
+ * -- a field and the codes built on it share streams, workspaces and plan caches -- must be serialised
+ * by the caller.  The error text is thread-local; the launch counter is atomic; the bchfft_profile_*
+ * calls are a single-threaded measurement aid.
  */
 #ifndef BCHFFT_CUDA_H
 #define BCHFFT_CUDA_H
@@ -38,6 +44,8 @@ typedef struct bchfft_code bchfft_code;   /* per BCH code state on top of a fiel
 
 /* thread-local text of the last error returned on this thread */
 const char *bchfft_last_error(void);
+/* set this thread's error text (the host library moves a worker thread's message to its caller) */
+void bchfft_set_last_error(const char *text);
 /* number of visible CUDA devices (0 or negative status if none) */
 int bchfft_device_count(void);
 /* 1 when the library is the CPU emulator build used by the unit tests, 0 for the real CUDA build */
