@@ -106,6 +106,8 @@ class Host:
         L.bch_encode_batch.argtypes = [cp, ulp, ulp, C.c_size_t, C.c_uint32, C.c_size_t]
         L.bchfft_last_error.restype = C.c_char_p
         L.bchfft_host_shutdown.restype = None
+        L.bchfft_host_num_devices.restype = C.c_int
+        L.bchfft_host_num_contexts.restype = C.c_int
 
     def _check(self, rc, what):
         if rc:

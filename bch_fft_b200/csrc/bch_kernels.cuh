@@ -1277,11 +1277,17 @@ k_encode_wide(const uint64_t *__restrict__ data, uint32_t dwords, uint32_t data_
 // ok = 1, corrected = 0 for a clean word; L > t -> ok = 0, corrected = 0; otherwise corrected =
 // #roots and the bits are flipped iff #roots == L.  Flips outside the packed array (only
 // possible for shortened codes, where the reference writes out of bounds) are skipped.
+// patch_dst (optional): the caller's page-locked HOST array for these codewords, addressed by the
+// device (unified addressing).  Every 64-bit word a flip touched is then also written there, so the
+// host array ends up corrected without the 1 KiB-per-codeword device-to-host copy: at most t
+// eight-byte writes per codeword cross the bus instead (words nobody touched are already right --
+// the host array is where the received words came from).
 __global__ void k_correct(uint64_t *__restrict__ words, uint32_t words_per_cw, uint32_t batch,
                           const int32_t *__restrict__ flag, const uint32_t *__restrict__ Lin,
                           uint32_t tcap, const uint32_t *__restrict__ count,
                           const uint32_t *__restrict__ positions, uint32_t pos_stride,
-                          uint8_t *__restrict__ ok, uint32_t *__restrict__ corrected)
+                          uint8_t *__restrict__ ok, uint32_t *__restrict__ corrected,
+                          uint64_t *__restrict__ patch_dst)
 {
   const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
   if (cw >= batch) return;
@@ -1297,6 +1303,14 @@ __global__ void k_correct(uint64_t *__restrict__ words, uint32_t words_per_cw, u
         for (uint32_t i = 0; i < found; ++i) {
           const uint32_t p = positions[(size_t)cw * pos_stride + i];
           if ((p >> 6) < words_per_cw) w[p >> 6] ^= 1ull << (p & 63u);
+        }
+        if (patch_dst) {
+          // final values (two flips may share a word: both writes then carry the same value)
+          uint64_t *hw = patch_dst + (size_t)cw * words_per_cw;
+          for (uint32_t i = 0; i < found; ++i) {
+            const uint32_t p = positions[(size_t)cw * pos_stride + i];
+            if ((p >> 6) < words_per_cw) hw[p >> 6] = w[p >> 6];
+          }
         }
       }
     }

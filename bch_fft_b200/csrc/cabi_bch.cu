@@ -352,7 +352,7 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
 
 template <int M>
 static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words, size_t batch, uint8_t *d_ok,
-                      uint32_t *d_corrected, cudaStream_t st)
+                      uint32_t *d_corrected, cudaStream_t st, uint64_t *patch_dst = nullptr)
 {
   const uint32_t pos_stride = c->t + 1u;
   // Chunk the batch only to bound the scratch (about 5 d + t words per codeword).  The decode is
@@ -386,7 +386,8 @@ static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words
     BCHFFT_RUN(k_correct, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, wp, c->wpc,
                   (uint32_t)cnt, (const int32_t *)s.flag, (const uint32_t *)s.L, c->t,
                   (const uint32_t *)s.count, (const uint32_t *)s.positions, s.pos_stride,
-                  d_ok ? d_ok + i0 : (uint8_t *)nullptr, d_corrected ? d_corrected + i0 : (uint32_t *)nullptr);
+                  d_ok ? d_ok + i0 : (uint8_t *)nullptr, d_corrected ? d_corrected + i0 : (uint32_t *)nullptr,
+                  patch_dst ? patch_dst + i0 * c->wpc : (uint64_t *)nullptr);
   }
   return BCHFFT_OK;
 }
@@ -731,10 +732,31 @@ extern "C" int bchfft_bch_decode_dev(bchfft_code *c, uint64_t *d_words, size_t b
 }
 
 // Host-pointer entry point: the batch is cut into chunks that travel through up to three lanes
-// (stream + staging + scratch each), so the host->device copy of chunk i+1 and the device->host
-// copy of chunk i-1 overlap the decode of chunk i.  (Full overlap needs page-locked host memory;
-// with pageable memory the copies are staged by the driver and mostly serialise.)
+// (stream + staging + scratch each), so the host->device copy of chunk i+1 and the result traffic of
+// chunk i-1 overlap the decode of chunk i.  (Full overlap needs page-locked host memory; with pageable
+// memory the copies are staged by the driver and mostly serialise.)
+//
+// Results come back in one of two ways (BCHFFT_D2H_MODE = patch | words overrides the choice):
+//   patch  the caller's array is page-locked, i.e. addressable by the device: k_correct writes the (at
+//          most t) 64-bit words it changed straight into it, and only ok / corrected (5 bytes per
+//          codeword) are copied back -- the bus carries the received words in and a few dozen bytes
+//          per codeword out, instead of the whole 1 KiB both ways;
+//   words  pageable host memory: every decoded word is copied back (the reference's in-place
+//          contract needs nothing else).
 namespace bchfft {
+static uint64_t *device_alias_of_host(const void *host_ptr)
+{
+  const char *env = getenv("BCHFFT_D2H_MODE");
+  if (env && !strcmp(env, "words")) return nullptr;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) {
+    cudaGetLastError();   /* not an error for us: plain pageable memory on older runtimes */
+    return nullptr;
+  }
+  if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return nullptr;
+  return (uint64_t *)attr.devicePointer;
+}
+
 template <int M>
 static int decode_host_run(bchfft_code *c, uint64_t *words, size_t batch, uint8_t *ok, uint32_t *corrected)
 {
@@ -743,9 +765,10 @@ static int decode_host_run(bchfft_code *c, uint64_t *words, size_t batch, uint8_
   size_t per = env ? (size_t)atol(env) : ((size_t)64 << 20) / cw_bytes;
   per = per < 32 ? 32 : (per / 32) * 32;
   if (per > batch) per = (batch + 31) / 32 * 32;
-  int rc;
+  int rc = BCHFFT_OK;
   const char *lenv = getenv("BCHFFT_E2E_LANES");
   const int nlanes = (lenv && atoi(lenv) >= 1 && atoi(lenv) <= 3) ? atoi(lenv) : 3;
+  uint64_t *patch = device_alias_of_host(words);
   for (int l = 1; l <= nlanes; l++) {
     bchfft_code::WorkSet &w = c->work[l];
     if (!w.stream) BCHFFT_CUDA_TRY(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
@@ -753,21 +776,33 @@ static int decode_host_run(bchfft_code *c, uint64_t *words, size_t batch, uint8_
     if ((rc = w.ok.reserve(per))) return rc;
     if ((rc = w.corr.reserve(per * 4))) return rc;
   }
-  int lane = 1;
-  for (size_t i0 = 0; i0 < batch; i0 += per, lane = lane % nlanes + 1) {
+  auto enqueue = [&](size_t i0, int lane) -> int {
     const size_t cnt = batch - i0 < per ? batch - i0 : per;
     bchfft_code::WorkSet &w = c->work[lane];
     cudaStream_t st = w.stream;
     uint64_t *dw = (uint64_t *)w.words.p;
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(dw, words + i0 * c->wpc, cnt * cw_bytes, cudaMemcpyHostToDevice, st));
-    if ((rc = decode_run<M>(c, w, dw, cnt, (uint8_t *)w.ok.p, (uint32_t *)w.corr.p, st))) return rc;
-    BCHFFT_CUDA_TRY(cudaMemcpyAsync(words + i0 * c->wpc, dw, cnt * cw_bytes, cudaMemcpyDeviceToHost, st));
+    int r = decode_run<M>(c, w, dw, cnt, (uint8_t *)w.ok.p, (uint32_t *)w.corr.p, st,
+                          patch ? patch + i0 * c->wpc : (uint64_t *)nullptr);
+    if (r) return r;
+    if (!patch)
+      BCHFFT_CUDA_TRY(cudaMemcpyAsync(words + i0 * c->wpc, dw, cnt * cw_bytes, cudaMemcpyDeviceToHost, st));
     if (ok) BCHFFT_CUDA_TRY(cudaMemcpyAsync(ok + i0, w.ok.p, cnt, cudaMemcpyDeviceToHost, st));
     if (corrected)
       BCHFFT_CUDA_TRY(cudaMemcpyAsync(corrected + i0, w.corr.p, cnt * 4, cudaMemcpyDeviceToHost, st));
+    return BCHFFT_OK;
+  };
+  int lane = 1;
+  for (size_t i0 = 0; i0 < batch && !rc; i0 += per, lane = lane % nlanes + 1) rc = enqueue(i0, lane);
+  // drain every lane, also on an error: copies into the caller's buffers may still be in flight
+  for (int l = 1; l <= nlanes; l++) {
+    const cudaError_t e = cudaStreamSynchronize(c->work[l].stream);
+    if (e != cudaSuccess && !rc) {
+      set_error("bch decode: %s", cudaGetErrorString(e));
+      rc = BCHFFT_ERR_CUDA;
+    }
   }
-  for (int l = 1; l <= nlanes; l++) BCHFFT_CUDA_TRY(cudaStreamSynchronize(c->work[l].stream));
-  return BCHFFT_OK;
+  return rc;
 }
 }  // namespace bchfft
 

@@ -247,8 +247,7 @@ extern "C" int bchfft_additive_fft_host(bchfft_field *f, const uint32_t *polys, 
     if (results && (rc = l.out.reserve(per * (size_t)n * 4))) return rc;
     if (natural && (rc = l.aux.reserve(per * (size_t)n * 4))) return rc;
   }
-  int lane = 0;
-  for (size_t i0 = 0; i0 < batch; i0 += per, lane ^= 1) {
+  auto enqueue = [&](size_t i0, int lane) -> int {
     const size_t cnt = batch - i0 < per ? batch - i0 : per;
     bchfft_field::Lane &l = f->lanes[lane];
     uint32_t *d_in = (uint32_t *)l.in.p;
@@ -256,8 +255,8 @@ extern "C" int bchfft_additive_fft_host(bchfft_field *f, const uint32_t *polys, 
                                       (size_t)n * 4, cnt, cudaMemcpyHostToDevice, l.stream));
     uint32_t *d_res = results ? (uint32_t *)l.out.p : nullptr;
     uint32_t *d_nat = natural ? (uint32_t *)l.aux.p : nullptr;
-    rc = bchfft_additive_fft_dev_ws(f, l.ws, d_in, n, d_res, n, d_nat, n, num_terms, cnt, l.stream);
-    if (rc) return rc;
+    int r = bchfft_additive_fft_dev_ws(f, l.ws, d_in, n, d_res, n, d_nat, n, num_terms, cnt, l.stream);
+    if (r) return r;
     // the reference never writes entry n-1 of po_result (additive_fft.c:20): copy n-1 per row
     if (results)
       BCHFFT_CUDA_TRY(cudaMemcpy2DAsync(results + i0 * result_stride, result_stride * 4, d_res,
@@ -267,10 +266,20 @@ extern "C" int bchfft_additive_fft_host(bchfft_field *f, const uint32_t *polys, 
       BCHFFT_CUDA_TRY(cudaMemcpy2DAsync(natural + i0 * natural_stride, natural_stride * 4, d_nat,
                                         (size_t)n * 4, (size_t)n * 4, cnt, cudaMemcpyDeviceToHost,
                                         l.stream));
+    return BCHFFT_OK;
+  };
+  rc = BCHFFT_OK;
+  int lane = 0;
+  for (size_t i0 = 0; i0 < batch && !rc; i0 += per, lane ^= 1) rc = enqueue(i0, lane);
+  // drain both lanes, also on an error: copies into the caller's buffers may still be in flight
+  for (auto &l : f->lanes) {
+    const cudaError_t e = cudaStreamSynchronize(l.stream);
+    if (e != cudaSuccess && !rc) {
+      set_error("additive fft: %s", cudaGetErrorString(e));
+      rc = BCHFFT_ERR_CUDA;
+    }
   }
-  BCHFFT_CUDA_TRY(cudaStreamSynchronize(f->lanes[0].stream));
-  BCHFFT_CUDA_TRY(cudaStreamSynchronize(f->lanes[1].stream));
-  return BCHFFT_OK;
+  return rc;
 }
 
 #ifdef BCHFFT_TRACE

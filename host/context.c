@@ -200,6 +200,8 @@ static void* shard_worker(void* p)
 int bchfft_host_run_sharded(size_t count, size_t min_per_device, bchfft_shard_fn fn, void* arg)
 {
   int g = bchfft_host_num_devices();
+  const char* menv = getenv("BCHFFT_MIN_PER_DEVICE");   /* test hook: split small batches too */
+  if (menv && atol(menv) >= 1) min_per_device = (size_t) atol(menv);
   if (min_per_device < 1) min_per_device = 1;
   if ((size_t) g > count / min_per_device) g = (int) (count / min_per_device);
   if (g <= 1) return fn(0, 0, count, arg);
@@ -239,6 +241,15 @@ int bchfft_host_run_sharded(size_t count, size_t min_per_device, bchfft_shard_fn
   }
   if (status && err != jobs[0].err) bchfft_set_last_error(err);
   return status;
+}
+
+/* number of cached device contexts (fields + codes, all devices) */
+int bchfft_host_num_contexts(void)
+{
+  pthread_mutex_lock(&g_cache_lock);
+  const int n = g_num_fields + g_num_codes;
+  pthread_mutex_unlock(&g_cache_lock);
+  return n;
 }
 
 /* release every cached device context (optional; for leak checkers and tests) */

@@ -19,6 +19,7 @@ void bchfft_host_unlock_slot(int slot);
 bchfft_field* bchfft_host_field(TfiniteField* p_f, int slot, int* status);
 bchfft_code* bchfft_host_code(TbchCode* p_code, int slot, int* status);
 void bchfft_host_shutdown(void);
+int bchfft_host_num_contexts(void);
 
 /* Batch driver: cuts [0, count) into one contiguous range per device (multiples of 32 items, at
  * least min_per_device each) and calls fn(slot, lo, hi, arg) for every range from its own host thread

@@ -592,3 +592,61 @@ def test_emu_gen_code_rejects_what_the_device_cannot_decode(emu_libs):
     for n, d in ((255, 2), (255, 1), ((1 << 26) - 1, 5)):
         with pytest.raises(ValueError):
             host.bch_gen_code(n, d)
+
+
+def test_emu_decode_result_modes_agree(emu_libs, port):
+    """bch_decode_batch returns results either by patching the caller's (device-addressable) array with
+    the words k_correct changed, or by copying every word back (BCHFFT_D2H_MODE=words); both must give
+    the reference's words, untouched failures included"""
+    _, host = emu_libs
+    n, t, B = 1023, 10, 300
+    code, pc = host.bch_gen_code(n, 2 * t + 1), port.code(n, t)
+    words = _words_for(pc, n, t, B, np.random.default_rng(99))
+    rok, rcorr, rout = pc.decode_batch(words)
+    try:
+        for mode in ("patch", "words"):
+            os.environ["BCHFFT_D2H_MODE"] = mode
+            ok, corr, out = code.decode_batch(words)
+            assert (ok == rok).all() and (corr == rcorr).all() and (out == rout).all(), mode
+    finally:
+        os.environ.pop("BCHFFT_D2H_MODE", None)
+
+
+def test_emu_in_library_multi_device_sharding(emu_libs, port):
+    """host library with a set of devices: batch calls cut the caller's arrays into one
+    contiguous range per device, one host thread each; results equal the single-device ones.  The
+    emulator pretends to have three devices (BCHFFT_EMU_DEVICES); small BCHFFT_MIN_PER_DEVICE forces the
+    split on a small batch."""
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from bch_fft_b200 import api, synth\n"
+        "from oracle.pyoracle import Port\n"
+        "from tests.conftest import EMU_HOST\n"
+        "from tests.test_emu_kernels import _words_for\n"
+        "host, P = api.Host(EMU_HOST), Port()\n"
+        "assert host.lib.bchfft_host_num_devices() == 3\n"
+        "n, t, B = 255, 8, 1000\n"
+        "code, pc = host.bch_gen_code(n, 2 * t + 1), P.code(n, t)\n"
+        "words = _words_for(pc, n, t, B, np.random.default_rng(5))\n"
+        "ok, corr, out = code.decode_batch(words)\n"
+        "rok, rcorr, rout = pc.decode_batch(words)\n"
+        "assert (ok == rok).all() and (corr == rcorr).all() and (out == rout).all()\n"
+        "k = code.data_bits; dw = (k + 63) // 64\n"
+        "data = synth.splitmix64(3, B * dw).reshape(B, dw)\n"
+        "enc = code.encode_batch(data, k)\n"
+        "bits = lambda i: ((data[i][:, None] >> np.arange(64, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.uint32).reshape(-1)[:k]\n"
+        "for i in (0, 399, 400, 999): assert (enc[i] == pc.encode(bits(i))).all()\n"
+        "m = 8; f = host.create_binary_finite_field(m)\n"
+        "polys = synth.random_polys(m, 200, 9)\n"
+        "res = f.additive_fft_batch(polys, 255)\n"
+        "mul = f.multiplicative_fft_batch(polys, 255)\n"
+        "for b in (0, 63, 64, 127, 128, 199):\n"
+        "    assert (res[b] == P.additive_fft(m, polys[b], 255)[0]).all() and (mul[b] == res[b]).all()\n"
+        "print('contexts', host.lib.bchfft_host_num_contexts())\n")
+    env = dict(os.environ, BCHFFT_EMU_DEVICES="3", BCHFFT_MIN_PER_DEVICE="64")
+    env.pop("BCHFFT_DEVICE", None)
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    # one field (GF(2^8)) + one code context per device
+    assert "contexts 6" in res.stdout, res.stdout

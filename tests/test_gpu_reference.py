@@ -252,3 +252,93 @@ def test_encode_batch_vs_reference(gpu_libs, ref, n, t):
         out = code.encode_batch(packed, nbits)
         for b in (0, 1, 2, 33, B - 1):
             assert (out[b] == rc.encode(bits[b])).all(), (n, t, nbits, b)
+
+
+# ---- end-to-end result modes, device sets ----------------------------------------------------------
+def _pinned_array(cabi, shape, dtype):
+    import ctypes as C
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    _lib.check(cabi, cabi.bchfft_pinned_alloc(nbytes, C.byref(p)), "pinned_alloc")
+    buf = (C.c_ubyte * nbytes).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), p
+
+
+def test_decode_patch_mode_on_pinned_host_memory(gpu_libs, ref):
+    """bch_decode_batch on a page-locked array: k_correct patches the changed 64-bit words straight into
+    the caller's array and only ok / corrected are copied back (BCHFFT_D2H_MODE=words: every word is
+    copied back).  Both modes, and pageable memory, against the reference -- 50000 words incl. failures
+    (left untouched), bit-0 quirk, two errors in one 64-bit word."""
+    import ctypes as C
+    import os
+    cabi, host = gpu_libs
+    n, t, B = 8191, 16, 50000
+    code, rc = host.bch_gen_code(n, 2 * t + 1), ref.code(n, t)
+    bits = (synth.splitmix64(0xD2, 64 * code.data_bits) & np.uint64(1)).astype(np.uint32)
+    pool = np.stack([rc.encode(b) for b in bits.reshape(64, -1)])
+    words, _ = synth.corrupt_codewords(pool, n, t, B, 0xD2, beyond_fraction=0.03)
+    words[7] = pool[3]
+    flip(words[7], 128), flip(words[7], 129), flip(words[7], 0)
+    rok, rcorr, rout, _ = rc.decode_batch_mt(words, _cores())
+    pw, hp = _pinned_array(cabi, words.shape, np.uint64)
+    ulp = C.POINTER(C.c_ulong)
+    try:
+        for mode in ("patch", "words"):
+            os.environ["BCHFFT_D2H_MODE"] = mode
+            pw[:] = words
+            ok = np.zeros(B, np.uint8)
+            corr = np.zeros(B, np.uint32)
+            rcode = host.lib.bch_decode_batch(C.byref(code.c), C.cast(hp.value, ulp), B,
+                                              ok.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                              corr.ctypes.data_as(C.POINTER(C.c_uint32)))
+            assert rcode == 0
+            assert (ok == rok).all() and (corr == rcorr).all() and (pw == rout).all(), mode
+    finally:
+        os.environ.pop("BCHFFT_D2H_MODE", None)
+        cabi.bchfft_pinned_free(hp)
+    ok, corr, out = code.decode_batch(words)          # pageable numpy memory
+    assert (ok == rok).all() and (corr == rcorr).all() and (out == rout).all()
+
+
+def test_in_library_multi_gpu_sharding(gpu_libs, ref):
+    """SURVEY 8e inside the library: with several devices a batch call drives one host thread per GPU on
+    contiguous ranges of the caller's single array (the array is the gather).  Needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    cabi, _ = gpu_libs
+    ndev = cabi.bchfft_device_count()
+    if ndev < 2:
+        pytest.skip("one GPU visible: the multi-device driver is covered by the emulator test "
+                    "test_emu_in_library_multi_device_sharding")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from bch_fft_b200 import api, synth\n"
+        "from oracle import pyoracle\n"
+        "host, R = api.Host(), pyoracle.Ref()\n"
+        f"assert host.lib.bchfft_host_num_devices() == {ndev}\n"
+        "n, t, B = 8191, 16, 100000\n"
+        "code, rc = host.bch_gen_code(n, 2 * t + 1), R.code(n, t)\n"
+        "bits = (synth.splitmix64(0xD3, 64 * code.data_bits) & np.uint64(1)).astype(np.uint32)\n"
+        "pool = np.stack([rc.encode(b) for b in bits.reshape(64, -1)])\n"
+        "words, _ = synth.corrupt_codewords(pool, n, t, B, 0xD3, beyond_fraction=0.02)\n"
+        "ok, corr, out = code.decode_batch(words)\n"
+        "rok, rcorr, rout, _ = rc.decode_batch_mt(words, 16)\n"
+        "assert (ok == rok).all() and (corr == rcorr).all() and (out == rout).all()\n"
+        "f = host.create_binary_finite_field(16)\n"
+        "polys = synth.random_polys(16, 512, 0xD4)\n"
+        "res = f.additive_fft_batch(polys, 65535)\n"
+        "pick = list(range(0, 512, 37)) + [511]\n"
+        "want, _ = R.additive_fft_batch_mt(16, polys[pick], 65535, 16)\n"
+        "assert (res[pick] == want).all()\n"
+        "mul = f.multiplicative_fft_batch(polys, 65535)\n"
+        "assert (mul == res).all()\n"
+        "print('contexts', host.lib.bchfft_host_num_contexts())\n")
+    env = dict(os.environ, BCHFFT_DEVICES="all", BCHFFT_MIN_PER_DEVICE="64")
+    env.pop("BCHFFT_DEVICE", None)
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=root)
+    assert res.returncode == 0, res.stderr[-3000:]
+    # per device: GF(2^13) field + code, GF(2^16) field
+    assert f"contexts {3 * ndev}" in res.stdout, res.stdout

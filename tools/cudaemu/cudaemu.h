@@ -29,7 +29,8 @@
 #define __noinline__
 #define __launch_bounds__(...)
 #define __restrict__ __restrict
-#define __shared__ static
+// per host thread: the multi-device driver of the host library runs one emulated device per thread
+#define __shared__ static thread_local
 #define __constant__ static
 #define __align__(x) __attribute__((aligned(x)))
 
@@ -59,7 +60,7 @@ struct State {
   void (*entry)(void *) = nullptr;
   void *arg = nullptr;
 };
-inline State &st() { static State s; return s; }
+inline State &st() { static thread_local State s; return s; }
 
 inline void trampoline()
 {
@@ -161,7 +162,14 @@ struct cudaDeviceProp { int multiProcessorCount; size_t sharedMemPerBlockOptin; 
 static inline const char *cudaGetErrorString(cudaError_t e) { return e ? "emulated CUDA error" : "no error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+// BCHFFT_EMU_DEVICES=k: pretend there are k devices (all of them this CPU), so that the host library's
+// multi-device sharding can be exercised without a GPU
+static inline cudaError_t cudaGetDeviceCount(int *n)
+{
+  const char *e = getenv("BCHFFT_EMU_DEVICES");
+  *n = (e && atoi(e) >= 1) ? atoi(e) : 1;
+  return cudaSuccess;
+}
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
@@ -197,6 +205,17 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { retur
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+// emulated "device" memory is host memory: every pointer is its own device alias
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void *devicePointer; void *hostPointer; };
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p)
+{
+  a->type = cudaMemoryTypeHost;
+  a->device = 0;
+  a->devicePointer = const_cast<void *>(p);
+  a->hostPointer = const_cast<void *>(p);
+  return cudaSuccess;
+}
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 
 // kernel<<<grid, block, smem, stream>>>(args...)  is written  BCHFFT_LAUNCH(kernel, grid, block, smem, stream, args...)
