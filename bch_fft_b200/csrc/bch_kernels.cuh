@@ -1277,6 +1277,7 @@ k_encode_wide(const uint64_t *__restrict__ data, uint32_t dwords, uint32_t data_
 // ok = 1, corrected = 0 for a clean word; L > t -> ok = 0, corrected = 0; otherwise corrected =
 // #roots and the bits are flipped iff #roots == L.  Flips outside the packed array (only
 // possible for shortened codes, where the reference writes out of bounds) are skipped.
+// flip_on_device = 0 skips the flips (the caller applies them from `positions`).
 // patch_dst (optional): the caller's page-locked HOST array for these codewords, addressed by the
 // device (unified addressing).  Every 64-bit word a flip touched is then also written there, so the
 // host array ends up corrected without the 1 KiB-per-codeword device-to-host copy: at most t
@@ -1287,7 +1288,7 @@ __global__ void k_correct(uint64_t *__restrict__ words, uint32_t words_per_cw, u
                           uint32_t tcap, const uint32_t *__restrict__ count,
                           const uint32_t *__restrict__ positions, uint32_t pos_stride,
                           uint8_t *__restrict__ ok, uint32_t *__restrict__ corrected,
-                          uint64_t *__restrict__ patch_dst)
+                          uint64_t *__restrict__ patch_dst, uint32_t flip_on_device)
 {
   const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
   if (cw >= batch) return;
@@ -1297,8 +1298,10 @@ __global__ void k_correct(uint64_t *__restrict__ words, uint32_t words_per_cw, u
     good = 0u;
     if (L <= tcap) {
       found = count[cw];
-      if (found == L) {
-        good = 1u;
+      if (found == L) good = 1u;
+      // flip_on_device = 0: the host applies the flips itself from the position lists ("positions"
+      // result mode of bchfft_bch_decode_host); only the verdict is needed here
+      if (found == L && flip_on_device) {
         uint64_t *w = words + (size_t)cw * words_per_cw;
         for (uint32_t i = 0; i < found; ++i) {
           const uint32_t p = positions[(size_t)cw * pos_stride + i];

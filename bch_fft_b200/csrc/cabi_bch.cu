@@ -2,6 +2,9 @@
 #include <stdlib.h>
 #include <type_traits>
 #include <string.h>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 #include "cabi_common.h"
 #include "bch_kernels.cuh"
@@ -31,6 +34,9 @@ struct bchfft_code {
     // root-search pass descriptors: a buffer of their own, allocated once, so that a growing
     // fwd_buf (DeviceBuffer::reserve frees and re-allocates) can never leave them stale
     bchfft::DeviceBuffer descs;
+    // "positions" result mode of the host entry point: page-locked staging for ok / corrected / position lists
+    bchfft::PinnedBuffer h_ok, h_corr, h_pos;
+    cudaEvent_t results_ready = nullptr;
     cudaStream_t stream = nullptr;
     int descs_t = -1, descs_kmax = -1;   // (t, kmax) of the descriptors currently uploaded
   } work[4];
@@ -350,9 +356,12 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
   return BCHFFT_OK;
 }
 
+// patch_dst: see k_correct.  h_positions (pinned host, [batch][t + 1]): "positions" result mode -- the
+// flips are left to the host, every chunk's position lists are copied there right after its verdict.
 template <int M>
 static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words, size_t batch, uint8_t *d_ok,
-                      uint32_t *d_corrected, cudaStream_t st, uint64_t *patch_dst = nullptr)
+                      uint32_t *d_corrected, cudaStream_t st, uint64_t *patch_dst = nullptr,
+                      uint32_t *h_positions = nullptr)
 {
   const uint32_t pos_stride = c->t + 1u;
   // Chunk the batch only to bound the scratch (about 5 d + t words per codeword).  The decode is
@@ -387,7 +396,10 @@ static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words
                   (uint32_t)cnt, (const int32_t *)s.flag, (const uint32_t *)s.L, c->t,
                   (const uint32_t *)s.count, (const uint32_t *)s.positions, s.pos_stride,
                   d_ok ? d_ok + i0 : (uint8_t *)nullptr, d_corrected ? d_corrected + i0 : (uint32_t *)nullptr,
-                  patch_dst ? patch_dst + i0 * c->wpc : (uint64_t *)nullptr);
+                  patch_dst ? patch_dst + i0 * c->wpc : (uint64_t *)nullptr, h_positions ? 0u : 1u);
+    if (h_positions)
+      BCHFFT_CUDA_TRY(cudaMemcpyAsync(h_positions + i0 * pos_stride, s.positions, cnt * pos_stride * sizeof(uint32_t),
+                                      cudaMemcpyDeviceToHost, st));
   }
   return BCHFFT_OK;
 }
@@ -703,6 +715,10 @@ extern "C" void bchfft_code_destroy(bchfft_code *c)
     w.fft_ws.release();
     w.fft_io.release();
     w.descs.release();
+    w.h_ok.release();
+    w.h_corr.release();
+    w.h_pos.release();
+    if (w.results_ready) cudaEventDestroy(w.results_ready);
     if (w.stream) cudaStreamDestroy(w.stream);
   }
   delete c;
@@ -736,18 +752,20 @@ extern "C" int bchfft_bch_decode_dev(bchfft_code *c, uint64_t *d_words, size_t b
 // chunk i-1 overlap the decode of chunk i.  (Full overlap needs page-locked host memory; with pageable
 // memory the copies are staged by the driver and mostly serialise.)
 //
-// Results come back in one of two ways (BCHFFT_D2H_MODE = patch | words overrides the choice):
-//   patch  the caller's array is page-locked, i.e. addressable by the device: k_correct writes the (at
-//          most t) 64-bit words it changed straight into it, and only ok / corrected (5 bytes per
-//          codeword) are copied back -- the bus carries the received words in and a few dozen bytes
-//          per codeword out, instead of the whole 1 KiB both ways;
-//   words  pageable host memory: every decoded word is copied back (the reference's in-place
-//          contract needs nothing else).
+// Results come back in one of three ways (BCHFFT_D2H_MODE = positions | words | patch picks one):
+//   positions  (default from 8192 codewords on) only the verdicts and the error-position lists cross the
+//          bus (73 bytes per codeword at t = 16 instead of 1 KiB); a few host threads apply the bit flips
+//          (add_bit, bch.c:539-542) to the caller's array while later chunks are still in flight.  The
+//          array already holds the received words -- it is where they were copied from -- so flipping the
+//          located bits completes bch_decode's in-place contract.
+//   words  every decoded word is copied back (small batches: no thread start-up cost).
+//   patch  page-locked caller arrays only: k_correct writes the 64-bit words it changed straight into the
+//          caller's array through unified addressing.  Measured (profiles/r2c_zerocopy_scatter_bench.jsonl):
+//          scattered 8-byte writes over PCIe run at 4*10^8 per second, i.e. no faster than copying whole
+//          words, and they slow the concurrent host-to-device copies down: kept as an option, not a default.
 namespace bchfft {
 static uint64_t *device_alias_of_host(const void *host_ptr)
 {
-  const char *env = getenv("BCHFFT_D2H_MODE");
-  if (env && !strcmp(env, "words")) return nullptr;
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) {
     cudaGetLastError();   /* not an error for us: plain pageable memory on older runtimes */
@@ -755,6 +773,114 @@ static uint64_t *device_alias_of_host(const void *host_ptr)
   }
   if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return nullptr;
   return (uint64_t *)attr.devicePointer;
+}
+
+// one chunk whose verdicts and position lists are (or will be, once `ready` fires) in pinned staging
+struct FlipJob {
+  uint64_t *words;            // caller's array, first codeword of the chunk
+  uint8_t *ok_out;            // caller's arrays (may be null)
+  uint32_t *corr_out;
+  const uint8_t *ok;          // staging
+  const uint32_t *corr, *pos;
+  size_t cnt;
+  cudaEvent_t ready;
+  int lane;
+};
+
+// The host threads of one bchfft_bch_decode_host call in "positions" mode.  Every worker owns a fixed
+// slice of EVERY chunk, so the chunks complete in order and a lane's staging is free again as soon as all
+// workers have passed its chunk.
+struct FlipPool {
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<FlipJob> jobs;          // published jobs, in order
+  bool closed = false;
+  std::vector<size_t> done;           // per job: workers that finished it
+  int device = 0;
+  uint32_t wpc = 0, pos_stride = 0;
+  size_t nworkers = 0;
+
+  void worker(size_t me)
+  {
+    cudaSetDevice(device);
+    for (size_t k = 0;; k++) {
+      FlipJob j;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return k < jobs.size() || closed; });
+        if (k >= jobs.size()) return;
+        j = jobs[k];
+      }
+      cudaEventSynchronize(j.ready);
+      const size_t lo = j.cnt * me / nworkers, hi = j.cnt * (me + 1) / nworkers;
+      for (size_t i = lo; i < hi; i++) {
+        // pull the words the flips of codeword i + 8 will touch into the cache while i is handled
+        const size_t ahead = i + 8;
+        if (ahead < hi && j.ok[ahead]) {
+          const uint32_t na = j.corr[ahead];
+          for (uint32_t e = 0; e < na; e++) {
+            const uint32_t p = j.pos[ahead * pos_stride + e];
+            if ((p >> 6) < wpc) __builtin_prefetch(j.words + ahead * wpc + (p >> 6), 1, 0);
+          }
+        }
+        if (j.ok[i]) {                                   // corrected = L roots found: flip them (bch.c:539-542)
+          const uint32_t nf = j.corr[i];
+          uint64_t *w = j.words + i * wpc;
+          for (uint32_t e = 0; e < nf; e++) {
+            const uint32_t p = j.pos[i * pos_stride + e];
+            if ((p >> 6) < wpc) w[p >> 6] ^= 1ull << (p & 63u);
+          }
+        }
+      }
+      if (j.ok_out) memcpy(j.ok_out + lo, j.ok + lo, hi - lo);
+      if (j.corr_out) memcpy(j.corr_out + lo, j.corr + lo, (hi - lo) * sizeof(uint32_t));
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        done[k]++;
+      }
+      cv.notify_all();
+    }
+  }
+  void start(size_t n, int dev, uint32_t wpc_, uint32_t pos_stride_)
+  {
+    nworkers = n;
+    device = dev;
+    wpc = wpc_;
+    pos_stride = pos_stride_;
+    for (size_t i = 0; i < n; i++) threads.emplace_back([this, i] { worker(i); });
+  }
+  size_t publish(const FlipJob &j)
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    jobs.push_back(j);
+    done.push_back(0);
+    cv.notify_all();
+    return jobs.size() - 1;
+  }
+  void wait_done(size_t k)
+  {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return done[k] == nworkers; });
+  }
+  void finish()
+  {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      closed = true;
+    }
+    cv.notify_all();
+    for (auto &t : threads) t.join();
+    threads.clear();
+  }
+};
+
+static size_t flip_threads()
+{
+  const char *env = getenv("BCHFFT_FLIP_THREADS");
+  if (env && atoi(env) >= 1 && atoi(env) <= 64) return (size_t)atoi(env);
+  size_t n = std::thread::hardware_concurrency() / 4;
+  return n < 2 ? 2 : (n > 8 ? 8 : n);
 }
 
 template <int M>
@@ -768,24 +894,59 @@ static int decode_host_run(bchfft_code *c, uint64_t *words, size_t batch, uint8_
   int rc = BCHFFT_OK;
   const char *lenv = getenv("BCHFFT_E2E_LANES");
   const int nlanes = (lenv && atoi(lenv) >= 1 && atoi(lenv) <= 3) ? atoi(lenv) : 3;
-  uint64_t *patch = device_alias_of_host(words);
+  const char *menv = getenv("BCHFFT_D2H_MODE");
+  enum { WORDS, PATCH, POSITIONS } mode = batch >= 8192 ? POSITIONS : WORDS;
+  if (menv && !strcmp(menv, "words")) mode = WORDS;
+  else if (menv && !strcmp(menv, "positions")) mode = POSITIONS;
+  else if (menv && !strcmp(menv, "patch")) mode = PATCH;
+  uint64_t *patch = mode == PATCH ? device_alias_of_host(words) : nullptr;
+  if (mode == PATCH && !patch) mode = WORDS;             // pageable memory: the device cannot address it
+  const uint32_t pos_stride = c->t + 1u;
   for (int l = 1; l <= nlanes; l++) {
     bchfft_code::WorkSet &w = c->work[l];
     if (!w.stream) BCHFFT_CUDA_TRY(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     if ((rc = w.words.reserve(per * cw_bytes))) return rc;
     if ((rc = w.ok.reserve(per))) return rc;
     if ((rc = w.corr.reserve(per * 4))) return rc;
+    if (mode == POSITIONS) {
+      if (!w.results_ready) BCHFFT_CUDA_TRY(cudaEventCreateWithFlags(&w.results_ready, cudaEventDisableTiming));
+      if ((rc = w.h_ok.reserve(per))) return rc;
+      if ((rc = w.h_corr.reserve(per * 4))) return rc;
+      if ((rc = w.h_pos.reserve(per * (size_t)pos_stride * 4))) return rc;
+    }
   }
+  FlipPool pool;
+  if (mode == POSITIONS) pool.start(flip_threads(), c->f->device, c->wpc, pos_stride);
+  size_t lane_job[4] = {(size_t)-1, (size_t)-1, (size_t)-1, (size_t)-1};
   auto enqueue = [&](size_t i0, int lane) -> int {
     const size_t cnt = batch - i0 < per ? batch - i0 : per;
     bchfft_code::WorkSet &w = c->work[lane];
     cudaStream_t st = w.stream;
     uint64_t *dw = (uint64_t *)w.words.p;
+    if (mode == POSITIONS && lane_job[lane] != (size_t)-1) pool.wait_done(lane_job[lane]);   // staging free again
     BCHFFT_CUDA_TRY(cudaMemcpyAsync(dw, words + i0 * c->wpc, cnt * cw_bytes, cudaMemcpyHostToDevice, st));
     int r = decode_run<M>(c, w, dw, cnt, (uint8_t *)w.ok.p, (uint32_t *)w.corr.p, st,
-                          patch ? patch + i0 * c->wpc : (uint64_t *)nullptr);
+                          patch ? patch + i0 * c->wpc : (uint64_t *)nullptr,
+                          mode == POSITIONS ? (uint32_t *)w.h_pos.p : (uint32_t *)nullptr);
     if (r) return r;
-    if (!patch)
+    if (mode == POSITIONS) {
+      BCHFFT_CUDA_TRY(cudaMemcpyAsync(w.h_ok.p, w.ok.p, cnt, cudaMemcpyDeviceToHost, st));
+      BCHFFT_CUDA_TRY(cudaMemcpyAsync(w.h_corr.p, w.corr.p, cnt * 4, cudaMemcpyDeviceToHost, st));
+      BCHFFT_CUDA_TRY(cudaEventRecord(w.results_ready, st));
+      FlipJob j;
+      j.words = words + i0 * c->wpc;
+      j.ok_out = ok ? ok + i0 : nullptr;
+      j.corr_out = corrected ? corrected + i0 : nullptr;
+      j.ok = (const uint8_t *)w.h_ok.p;
+      j.corr = (const uint32_t *)w.h_corr.p;
+      j.pos = (const uint32_t *)w.h_pos.p;
+      j.cnt = cnt;
+      j.ready = w.results_ready;
+      j.lane = lane;
+      lane_job[lane] = pool.publish(j);
+      return BCHFFT_OK;
+    }
+    if (mode == WORDS)
       BCHFFT_CUDA_TRY(cudaMemcpyAsync(words + i0 * c->wpc, dw, cnt * cw_bytes, cudaMemcpyDeviceToHost, st));
     if (ok) BCHFFT_CUDA_TRY(cudaMemcpyAsync(ok + i0, w.ok.p, cnt, cudaMemcpyDeviceToHost, st));
     if (corrected)
@@ -802,6 +963,7 @@ static int decode_host_run(bchfft_code *c, uint64_t *words, size_t batch, uint8_
       rc = BCHFFT_ERR_CUDA;
     }
   }
+  if (mode == POSITIONS) pool.finish();                  // every published chunk is flipped before we return
   return rc;
 }
 }  // namespace bchfft

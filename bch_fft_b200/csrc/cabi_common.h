@@ -63,6 +63,14 @@ struct DeviceBuffer {
   void release();
 };
 
+// page-locked host staging (grow-only)
+struct PinnedBuffer {
+  void *p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need);
+  void release();
+};
+
 }  // namespace bchfft
 
 struct bchfft_field {

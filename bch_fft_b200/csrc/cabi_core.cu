@@ -37,6 +37,24 @@ void DeviceBuffer::release()
   bytes = 0;
 }
 
+int PinnedBuffer::reserve(size_t need)
+{
+  if (need <= bytes) return BCHFFT_OK;
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  bytes = 0;
+  BCHFFT_CUDA_TRY(cudaMallocHost(&p, need));
+  bytes = need;
+  return BCHFFT_OK;
+}
+
+void PinnedBuffer::release()
+{
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  bytes = 0;
+}
+
 int ensure_smem(const void *kernel, int device, size_t bytes)
 {
   // process-wide table: callers on different contexts / devices may run concurrently

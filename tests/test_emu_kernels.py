@@ -595,21 +595,28 @@ def test_emu_gen_code_rejects_what_the_device_cannot_decode(emu_libs):
 
 
 def test_emu_decode_result_modes_agree(emu_libs, port):
-    """bch_decode_batch returns results either by patching the caller's (device-addressable) array with
-    the words k_correct changed, or by copying every word back (BCHFFT_D2H_MODE=words); both must give
-    the reference's words, untouched failures included"""
+    """bch_decode_batch returns results in one of three ways (BCHFFT_D2H_MODE): position lists applied by
+    host threads, every word copied back, or the changed words patched into the caller's array by the
+    device; all must give the reference's words, untouched failures included"""
     _, host = emu_libs
     n, t, B = 1023, 10, 300
     code, pc = host.bch_gen_code(n, 2 * t + 1), port.code(n, t)
     words = _words_for(pc, n, t, B, np.random.default_rng(99))
     rok, rcorr, rout = pc.decode_batch(words)
     try:
-        for mode in ("patch", "words"):
+        for mode in ("positions", "patch", "words"):
             os.environ["BCHFFT_D2H_MODE"] = mode
             ok, corr, out = code.decode_batch(words)
             assert (ok == rok).all() and (corr == rcorr).all() and (out == rout).all(), mode
+        # five chunks through three lanes: the staging of a lane is reused while host threads still flip
+        os.environ["BCHFFT_D2H_MODE"] = "positions"
+        os.environ["BCHFFT_E2E_CHUNK"] = "64"
+        os.environ["BCHFFT_FLIP_THREADS"] = "3"
+        ok, corr, out = code.decode_batch(words)
+        assert (ok == rok).all() and (corr == rcorr).all() and (out == rout).all()
     finally:
-        os.environ.pop("BCHFFT_D2H_MODE", None)
+        for k in ("BCHFFT_D2H_MODE", "BCHFFT_E2E_CHUNK", "BCHFFT_FLIP_THREADS"):
+            os.environ.pop(k, None)
 
 
 def test_emu_in_library_multi_device_sharding(emu_libs, port):

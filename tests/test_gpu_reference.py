@@ -265,10 +265,11 @@ def _pinned_array(cabi, shape, dtype):
 
 
 def test_decode_patch_mode_on_pinned_host_memory(gpu_libs, ref):
-    """bch_decode_batch on a page-locked array: k_correct patches the changed 64-bit words straight into
-    the caller's array and only ok / corrected are copied back (BCHFFT_D2H_MODE=words: every word is
-    copied back).  Both modes, and pageable memory, against the reference -- 50000 words incl. failures
-    (left untouched), bit-0 quirk, two errors in one 64-bit word."""
+    """bch_decode_batch on a page-locked array in its three result modes (BCHFFT_D2H_MODE): positions
+    (verdicts + error positions come back, host threads flip the bits: the default for large batches),
+    words (every word is copied back), patch (k_correct writes the changed words into the caller's array).
+    All modes, and pageable memory, against the reference -- 50000 words incl. failures (left untouched),
+    bit-0 quirk, two errors in one 64-bit word."""
     import ctypes as C
     import os
     cabi, host = gpu_libs
@@ -283,7 +284,7 @@ def test_decode_patch_mode_on_pinned_host_memory(gpu_libs, ref):
     pw, hp = _pinned_array(cabi, words.shape, np.uint64)
     ulp = C.POINTER(C.c_ulong)
     try:
-        for mode in ("patch", "words"):
+        for mode in ("positions", "patch", "words"):
             os.environ["BCHFFT_D2H_MODE"] = mode
             pw[:] = words
             ok = np.zeros(B, np.uint8)
