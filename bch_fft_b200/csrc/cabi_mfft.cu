@@ -3,6 +3,7 @@
 
 #include "cabi_common.h"
 #include "mfft_kernels.cuh"
+#include "mfft16_kernels.cuh"
 
 namespace bchfft {
 
@@ -10,7 +11,64 @@ struct MfftState {
   std::vector<uint32_t> factors;   // prime factors of 2^m - 1, descending
   uint32_t *d_perm_id = nullptr;   // identity permutation
   uint32_t *d_perm_zero = nullptr; // all zeros (constant polynomial)
+  // GF(2^16) fast path (mfft16_kernels.cuh): coset table k_s 2^i mod 257 and the normal-basis
+  // coordinates of the 257th roots of unity
+  uint32_t *d_cos16 = nullptr, *d_ctab = nullptr;
+  bool fast16 = false;
 };
+
+// tables of the cyclotomic 257-point transform; false when x^kNormalLog does not generate a normal basis
+// (cannot happen for the reference's GF(2^16); checked rather than assumed)
+static bool mfft16_tables(const bchfft_field *f, std::vector<uint32_t> &cos16, std::vector<uint32_t> &ctab)
+{
+  const uint32_t N = f->order;
+  const uint32_t *ex = f->h_exp.data(), *lg = f->h_log.data();
+  uint32_t conj[16];
+  conj[0] = ex[mf16::kNormalLog];
+  for (int b = 1; b < 16; b++) conj[b] = ex[(2u * lg[conj[b - 1]]) % N];
+  // echelon form of the conjugates, each row with the combination of conjugates that produced it
+  uint32_t ech_v[16] = {0}, ech_c[16] = {0};
+  for (int b = 0; b < 16; b++) {
+    uint32_t v = conj[b], comb = 1u << b;
+    for (int bit = 15; bit >= 0 && v; bit--) {
+      if (!((v >> bit) & 1u)) continue;
+      if (ech_v[bit]) {
+        v ^= ech_v[bit];
+        comb ^= ech_c[bit];
+      } else {
+        ech_v[bit] = v;
+        ech_c[bit] = comb;
+        v = 0;
+      }
+    }
+  }
+  for (int bit = 0; bit < 16; bit++)
+    if (!ech_v[bit]) return false;
+  ctab.assign(257, 0u);
+  for (uint32_t e = 0; e < 257u; e++) {
+    uint32_t z = ex[(255u * e) % N], out = 0u;
+    for (int bit = 15; bit >= 0; bit--)
+      if ((z >> bit) & 1u) {
+        z ^= ech_v[bit];
+        out ^= ech_c[bit];
+      }
+    ctab[e] = out;
+  }
+  cos16.assign(256, 0u);
+  std::vector<bool> seen(257, false);
+  uint32_t s = 0;
+  for (uint32_t k = 1; k < 257u && s < 16u; k++) {
+    if (seen[k]) continue;
+    uint32_t v = k;
+    for (uint32_t i = 0; i < 16u; i++) {
+      cos16[s * 16u + i] = v;
+      seen[v] = true;
+      v = (2u * v) % 257u;
+    }
+    s++;
+  }
+  return s == 16u;
+}
 
 // prime factorisations of 2^m - 1 for m = 8..26 (the reference's table,
 // libfft/multiplicative_fft.c:11-33); other m: unknown -> the reference returns 1
@@ -54,8 +112,19 @@ static int mfft_run(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride
       delete st;
       return BCHFFT_ERR_CUDA;
     }
-    cudaMemcpy(st->d_perm_id, id.data(), (size_t)n * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(st->d_perm_zero, zero.data(), (size_t)n * 4, cudaMemcpyHostToDevice);
+    BCHFFT_CUDA_TRY(cudaMemcpy(st->d_perm_id, id.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    BCHFFT_CUDA_TRY(cudaMemcpy(st->d_perm_zero, zero.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    if (M == 16) {
+      std::vector<uint32_t> cos16, ctab;
+      if (mfft16_tables(f, cos16, ctab) &&
+          cudaMalloc((void **)&st->d_cos16, cos16.size() * 4) == cudaSuccess &&
+          cudaMalloc((void **)&st->d_ctab, ctab.size() * 4 + 16) == cudaSuccess) {
+        BCHFFT_CUDA_TRY(cudaMemcpy(st->d_cos16, cos16.data(), cos16.size() * 4, cudaMemcpyHostToDevice));
+        BCHFFT_CUDA_TRY(cudaMemcpy(st->d_ctab, ctab.data(), ctab.size() * 4, cudaMemcpyHostToDevice));
+        st->fast16 = true;
+      }
+    }
+    BCHFFT_CUDA_TRY(cudaDeviceSynchronize());   // tables in place before a non-blocking stream reads them
     f->mfft = st;
   }
   MfftState *st = (MfftState *)f->mfft;
@@ -73,6 +142,10 @@ static int mfft_run(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride
   }
   const size_t slab_words = (size_t)n * PS;
   const size_t nslabs = (batch + 31) / 32;
+  // GF(2^16) with more coefficients than the 3 x 5 x 17 stages alone cover: Good-Thomas 255 x 257 with the
+  // cyclotomic 257-point transform (mfft16_kernels.cuh)
+  const char *fenv = getenv("BCHFFT_MFFT_FAST");
+  const bool fast16 = M == 16 && st->fast16 && ncoef > 255u && !(fenv && atoi(fenv) == 0);
   size_t chunk = f->chunk_bytes / (2 * slab_words * 4);
   if (chunk < 1) chunk = 1;
   if (chunk > nslabs) chunk = nslabs;
@@ -85,6 +158,27 @@ static int mfft_run(bchfft_field *f, const uint32_t *d_polys, size_t poly_stride
     const uint32_t items = (uint32_t)((batch - s0 * 32 < cs * 32) ? batch - s0 * 32 : cs * 32);
     BCHFFT_RUN(k_bitslice_in<M>, dim3((n + 127) / 128, (unsigned)cs), dim3(128), 0, stream,
                d_polys + s0 * 32 * poly_stride, poly_stride, items, ncoef, f->m, buf[0]);
+    if (fast16) {
+      if constexpr (M == 16) {
+        const size_t smem1 = sizeof(uint32_t) * (2 * 16 * mf16::kAS + 256 + 257 + 8);
+        const size_t smem2 = sizeof(uint32_t) * (2 * 16 * mf16::kAS);
+#ifdef BCHFFT_EMU
+        const unsigned nt = 32;
+#else
+        const unsigned nt = 256;
+#endif
+        BCHFFT_ENSURE_SMEM(mf16::k_mfft16_p257, f->device, smem1);
+        BCHFFT_ENSURE_SMEM(mf16::k_mfft16_p255, f->device, smem2);
+        BCHFFT_RUN(mf16::k_mfft16_p257, dim3(255, (unsigned)cs), dim3(nt), smem1, stream, (const uint32_t *)buf[0],
+                   buf[1], slab_words, (const uint32_t *)st->d_cos16, (const uint32_t *)st->d_ctab);
+        BCHFFT_RUN(mf16::k_mfft16_p255, dim3(257, (unsigned)cs), dim3(nt), smem2, stream, (const uint32_t *)buf[1],
+                   buf[0], slab_words);
+        BCHFFT_RUN(k_gather_out<M>, dim3((N + 127) / 128, (unsigned)cs), dim3(128), 0, stream,
+                   (const uint32_t *)buf[0], slab_words, (const uint32_t *)st->d_perm_id, N,
+                   d_evals + s0 * 32 * eval_stride, eval_stride, items);
+      }
+      continue;
+    }
     int cur = 0;
     for (size_t li = 0; li < levels.size(); li++) {
       const Level &lv = levels[li];
@@ -112,6 +206,8 @@ extern "C" void bchfft_mfft_release(bchfft_field *f)
   MfftState *st = (MfftState *)f->mfft;
   cudaFree(st->d_perm_id);
   cudaFree(st->d_perm_zero);
+  cudaFree(st->d_cos16);
+  cudaFree(st->d_ctab);
   delete st;
   f->mfft = nullptr;
 }

@@ -657,3 +657,19 @@ def test_emu_in_library_multi_device_sharding(emu_libs, port):
     assert res.returncode == 0, res.stderr[-2000:]
     # one field (GF(2^8)) + one code context per device
     assert "contexts 6" in res.stdout, res.stdout
+
+
+def test_emu_multiplicative_fft_gf2_16_fast_path(emu_libs, port, ref):
+    """GF(2^16): Good-Thomas 255 x 257, cyclotomic 257-point transforms, 3 x 5 x 17 prime-factor transforms
+    (mfft16_kernels.cuh) against the restatement and the unmodified reference, full length and truncated
+    coefficient counts on both sides of the fast path's threshold (255)"""
+    _, host = emu_libs
+    m, n = 16, 1 << 16
+    f = host.create_binary_finite_field(m)
+    polys = synth.random_polys(m, 33, 0xC5)
+    full = f.multiplicative_fft_batch(polys, n - 1)
+    assert (full[0] == port.mult_fft(m, polys[0, : n - 1])).all()
+    assert (full[32] == ref.mult_fft(m, polys[32, : n - 1])).all()
+    for nc in (255, 256, 40000):
+        got = f.multiplicative_fft_batch(polys, nc)
+        assert (got[32] == ref.mult_eval(m, polys[32], nc)).all(), nc
