@@ -360,21 +360,18 @@ __global__ void k_syn_from_fft(const uint32_t *__restrict__ res, uint32_t res_st
 //        With acc != nullptr (decode pipeline) the kernel also does k_syn_finish's job: it builds
 //        its syndrome column straight from the bitsliced accumulators (S_2j = S_j^2 through the
 //        tables), writes flag[], and the global syndrome array is never touched.
-// LPC = lanes per codeword (SM only; a power of two up to 32): the LPC lanes of a group split the
-// coefficient index j modulo LPC -- 1/LPC of the sequential work per codeword and 1/LPC of the shared
-// memory per thread, so that the (4 d + 3) 16-bit entries per codeword still fit next to the tables when t
-// is large (t = 64: LPC = 8, t = 200: LPC = 16; without that those codes fall back to global scratch and
-// run at L2 latency).  One XOR reduction (discrepancy) and at most one max reduction (degree after
-// cancellation) per iteration go through warp shuffles.  `cs`, the stride between coefficient rows, is
-// padded by the host so that the LPC rows one warp touches fall on disjoint banks.
+// LPC = lanes per codeword (SM only; 2 on the GPU): the two lanes of a pair split the coefficient
+// index by parity -- half the sequential work per codeword, and half the shared memory per thread,
+// so three CTAs are resident instead of two.  Rows are padded by 16 entries so that rows j and j+1
+// of one warp's codewords fall on disjoint banks.
 template <int M, bool SM, int LPC>
 __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ flag, uint32_t d,
                      uint32_t batch, const uint32_t *__restrict__ gexp, const uint32_t *__restrict__ glog,
                      uint32_t *__restrict__ bm, uint32_t *__restrict__ elp, uint32_t *__restrict__ Lout,
                      const uint32_t *__restrict__ acc, const uint32_t *__restrict__ parity, uint32_t nodd,
-                     uint32_t elp_limit, uint32_t cs_sm)
+                     uint32_t elp_limit)
 {
-  static_assert(LPC == 1 || (SM && LPC <= 32 && (LPC & (LPC - 1)) == 0), "lane groups need the shared-memory variant");
+  static_assert(LPC == 1 || (LPC == 2 && SM), "lane pairs need the shared-memory variant");
   typedef typename std::conditional<SM, uint16_t, uint32_t>::type coef_t;
   const uint32_t order = (1u << M) - 1u;
   BCHFFT_DYN_SMEM(uint16_t, tabs);
@@ -382,32 +379,28 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
   const uint32_t per_cta = blockDim.x / LPC;
   const uint32_t cwl = threadIdx.x / LPC, sub = threadIdx.x % LPC;
   const uint32_t cw = blockIdx.x * per_cta + cwl;
-  // the LPC lanes of this codeword within the warp
-  const uint32_t pairmask = LPC == 32 ? 0xFFFFFFFFu
-                          : LPC >= 2 ? (((1u << (LPC & 31)) - 1u) << (threadIdx.x & 31u & ~(uint32_t)(LPC - 1))) : 0u;
+  const uint32_t pairmask = LPC == 2 ? (3u << (threadIdx.x & 30u)) : 0u;
   auto pair_sync = [&]() {
 #ifndef BCHFFT_EMU
-    if (LPC >= 2) __syncwarp(pairmask);
+    if (LPC == 2) __syncwarp(pairmask);
 #endif
   };
   auto pair_xor = [&](uint32_t v) -> uint32_t {
 #ifndef BCHFFT_EMU
-#pragma unroll
-    for (int o = LPC / 2; o >= 1; o >>= 1) v ^= __shfl_xor_sync(pairmask, v, o);
+    if (LPC == 2) v ^= __shfl_xor_sync(pairmask, v, 1);
 #endif
     return v;
   };
   auto pair_max = [&](int v) -> int {
 #ifndef BCHFFT_EMU
-#pragma unroll
-    for (int o = LPC / 2; o >= 1; o >>= 1) {
-      const int w = __shfl_xor_sync(pairmask, v, o);
-      v = w > v ? w : v;
+    if (LPC == 2) {
+      const int o = __shfl_xor_sync(pairmask, v, 1);
+      v = o > v ? o : v;
     }
 #endif
     return v;
   };
-  const size_t cs = SM ? (size_t)cs_sm : (size_t)batch;   // stride between coefficients
+  const size_t cs = SM ? (size_t)(per_cta + (LPC == 2 ? 16u : 0u)) : (size_t)batch;   // stride between coefficients
   const size_t bs = (size_t)(d + 1) * cs;                                              // stride between buffers
   coef_t *A, *B, *C;
   const coef_t *s;
