@@ -9,7 +9,7 @@
 //   k_bm           Berlekamp-Massey, one thread per codeword (bch.c:328-404), shared-memory resident
 //                  for small fields
 //   k_bucket / k_elp_fwd[_u]   sort by locator degree, forward phase of the truncated FFT
-//   k_locate_u     error-locator evaluation at every field point, K <= 5 levels, warp lanes = slabs,
+//   k_locate_u     error-locator evaluation at every field point, K <= 7 levels, warp lanes = slabs,
 //                  warp-uniform multipliers (bch.c:406-490)
 //   k_locate       same result, general path (tile engine, lanes = positions)
 //   k_correct      ok / corrected bookkeeping and the bit flips (bch.c:531-561)
@@ -150,8 +150,26 @@ __device__ __forceinline__ void lfsr_field_step(uint32_t (&s)[M], uint32_t in)
 }
 
 // A CTA takes TWO slabs: their plane words are interleaved (uint2 per position), so that one
-// index update and one 64-bit shared load feed two LFSRs.  grid = ceil(slabs / 2); dynamic smem =
-// 2 * (ceil(order / 32) * 33 + nodd * M) words.
+// index update and one 64-bit shared load feed two LFSRs.  The position index is kept as a byte
+// offset (8 p), so a step costs three integer operations and one LDS.64 besides the two LFSRs.
+// grid = ceil(slabs / 2); dynamic smem = 2 * (32 * ceil(order / 32) + nodd * M) words.
+//
+// Phase A (transpose into plane words): thread = (slab, group of 32 positions); the 32 lanes of a
+// warp own 32 consecutive groups, i.e. addresses 256 bytes apart, so every lane stores its plane
+// words in an order rotated by its lane number (a five-stage barrel rotation of the register array).
+// Phase B: the 32 chunks of one class are the 32 lanes of one warp, so the class's remainder is one
+// warp XOR-reduction per plane; nothing else ever writes that accumulator.
+__device__ __forceinline__ uint32_t warp_xor(uint32_t v)
+{
+#ifdef BCHFFT_EMU
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v ^= __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+#else
+  return __reduce_xor_sync(0xFFFFFFFFu, v);
+#endif
+}
+
 template <int M>
 __global__ void __launch_bounds__(BCHFFT_NT_SYN, BCHFFT_MINB_SYNP)
 k_syndrome_p(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint32_t length_bits,
@@ -165,13 +183,13 @@ k_syndrome_p(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint
   const uint32_t nslabs = (batch + 31u) >> 5;
   const uint32_t ngrp = (order + 31u) / 32u;          // 32-position groups of the codeword
   uint2 *planes = reinterpret_cast<uint2 *>(smem);
-  uint32_t *sacc = smem + 2u * ngrp * 33u;             // [2][nodd][M]
+  uint32_t *sacc = smem + 2u * ngrp * 32u;             // [2][nodd][M]
   __shared__ uint32_t s_par[2];
   if (threadIdx.x < 2) s_par[threadIdx.x] = 0u;
-  for (uint32_t i = threadIdx.x; i < 2u * nodd * M; i += blockDim.x) sacc[i] = 0u;
   __syncthreads();
 
   // phase A: transpose 32 codewords x 32 positions blocks into plane words (both slabs)
+  const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t w = threadIdx.x; w < 2u * ngrp; w += blockDim.x) {
     const uint32_t which = w >= ngrp ? 1u : 0u, g = w - which * ngrp;
     const uint32_t slab = slab0 + which;
@@ -191,66 +209,86 @@ k_syndrome_p(const uint32_t *__restrict__ words32, uint32_t words32_per_cw, uint
     transpose32(x);
     const uint32_t vw = (g < words32_per_cw) ? vbits[g] : 0u;
     uint32_t par = 0u;
-    uint32_t *dst = reinterpret_cast<uint32_t *>(planes + g * 33u) + which;
 #pragma unroll
-    for (int b = 0; b < 32; ++b) {
-      dst[2 * b] = x[b];
-      par ^= x[b] & (0u - ((vw >> b) & 1u));
-    }
+    for (int b = 0; b < 32; ++b) par ^= x[b] & (0u - ((vw >> b) & 1u));
     if (par) atomicXor(&s_par[which], par);
+    // x[k] <- x[(k + lane) & 31]
+#pragma unroll
+    for (int sft = 0; sft < 5; ++sft) {
+      const bool on = (lane >> sft) & 1u;
+      uint32_t y[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) y[k] = on ? x[(k + (1 << sft)) & 31] : x[k];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) x[k] = y[k];
+    }
+    uint32_t *dst = reinterpret_cast<uint32_t *>(planes + g * 32u) + which;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) dst[2u * ((k + lane) & 31u)] = x[k];
   }
   __syncthreads();
 
-  // phase B
-  for (uint32_t item = threadIdx.x; item < nodd * 32u; item += blockDim.x) {
+  // phase B: uniform trip count for every thread (a warp is active as a whole)
+  const unsigned char *pbytes = reinterpret_cast<const unsigned char *>(planes);
+  constexpr uint32_t order8 = order * 8u;
+  for (uint32_t base = 0; base < nodd * 32u; base += blockDim.x) {
+    const uint32_t item = base + threadIdx.x;
+    const bool active = item < nodd * 32u;
     const uint32_t ji = item >> 5, q = item & 31u;
-    const uint32_t lc = lcs[ji];
-    const uint32_t e0 = q * lc, e1 = (e0 + lc < order) ? e0 + lc : order;   // chunk [e0, e1)
-    const uint32_t nsteps = e1 > e0 ? e1 - e0 : 0u;
-    const uint32_t step = jinv[ji];
-    uint32_t idx = start_idx[item];        // p(e1 - 1)
-    uint32_t s0[M], s1[M];
-#pragma unroll
-    for (int b = 0; b < M; ++b) s0[b] = s1[b] = 0u;
-    // descending e: s <- s X + c_(p(e));  p(e - 1) = p(e) - j^-1 mod order
-    // (all chunks of a class but the last have the same length, so the trip counts are warp-uniform)
-    const uint32_t main_steps = nsteps & ~7u, pro = nsteps - main_steps;
-    for (uint32_t k = 0; k < pro; ++k) {
-      const uint2 in = planes[idx + (idx >> 5)];
-      lfsr_field_step<M>(s0, in.x);
-      lfsr_field_step<M>(s1, in.y);
-      const uint32_t t = idx - step, t2 = t + order;
-      idx = t < t2 ? t : t2;   // unsigned min: t wrapped around 2^32 exactly when idx < step
-    }
-    for (uint32_t k = 0; k < main_steps; k += 8u) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint2 in = planes[idx + (idx >> 5)];
-        lfsr_field_step<M>(s0, in.x);
-        lfsr_field_step<M>(s1, in.y);
-        const uint32_t t = idx - step, t2 = t + order;
-        idx = t < t2 ? t : t2;
-      }
-    }
-    // shift by x^(q lc): out = sum_b s[b] * x^(q lc + b)
-    const uint32_t *fc = foldp + (size_t)item * M;
     uint32_t o0[M], o1[M];
 #pragma unroll
     for (int k = 0; k < M; ++k) o0[k] = o1[k] = 0u;
+    if (active) {
+      const uint32_t lc = lcs[ji];
+      const uint32_t e0 = q * lc, e1 = (e0 + lc < order) ? e0 + lc : order;   // chunk [e0, e1)
+      const uint32_t nsteps = e1 > e0 ? e1 - e0 : 0u;
+      const uint32_t step8 = jinv[ji] * 8u;
+      uint32_t idx8 = start_idx[item] * 8u;        // 8 p(e1 - 1)
+      uint32_t s0[M], s1[M];
 #pragma unroll
-    for (int b = 0; b < M; ++b) {
-      const uint32_t c = fc[b];
+      for (int b = 0; b < M; ++b) s0[b] = s1[b] = 0u;
+      // descending e: s <- s X + c_(p(e));  p(e - 1) = p(e) - j^-1 mod order
+      // (all chunks of a class but the last have the same length, so the trip counts are warp-uniform).
+      // The main loop takes M steps per trip: after M steps the rotating register names of the LFSR
+      // are back where they started, so the loop carries no register moves.
+      const uint32_t pro = nsteps % (uint32_t)M, main_steps = nsteps - pro;
+      for (uint32_t k = 0; k < pro; ++k) {
+        const uint2 in = *reinterpret_cast<const uint2 *>(pbytes + idx8);
+        lfsr_field_step<M>(s0, in.x);
+        lfsr_field_step<M>(s1, in.y);
+        const uint32_t t = idx8 - step8, t2 = t + order8;
+        idx8 = t < t2 ? t : t2;   // unsigned min: t wrapped around 2^32 exactly when idx8 < step8
+      }
+      for (uint32_t k = 0; k < main_steps; k += (uint32_t)M) {
 #pragma unroll
-      for (int k = 0; k < M; ++k) {
-        const uint32_t mask = 0u - ((c >> k) & 1u);
-        o0[k] ^= s0[b] & mask;
-        o1[k] ^= s1[b] & mask;
+        for (int u = 0; u < M; ++u) {
+          const uint2 in = *reinterpret_cast<const uint2 *>(pbytes + idx8);
+          lfsr_field_step<M>(s0, in.x);
+          lfsr_field_step<M>(s1, in.y);
+          const uint32_t t = idx8 - step8, t2 = t + order8;
+          idx8 = t < t2 ? t : t2;
+        }
+      }
+      // shift by x^(q lc): out = sum_b s[b] * x^(q lc + b)
+      const uint32_t *fc = foldp + (size_t)item * M;
+#pragma unroll
+      for (int b = 0; b < M; ++b) {
+        const uint32_t c = fc[b];
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          const uint32_t mask = 0u - ((c >> k) & 1u);
+          o0[k] ^= s0[b] & mask;
+          o1[k] ^= s1[b] & mask;
+        }
       }
     }
 #pragma unroll
     for (int k = 0; k < M; ++k) {
-      if (o0[k]) atomicXor(&sacc[ji * M + k], o0[k]);
-      if (o1[k]) atomicXor(&sacc[(nodd + ji) * M + k], o1[k]);
+      const uint32_t r0 = warp_xor(o0[k]), r1 = warp_xor(o1[k]);
+      if (active && q == 0u) {
+        sacc[ji * M + k] = r0;
+        sacc[(nodd + ji) * M + k] = r1;
+      }
     }
   }
   __syncthreads();
@@ -360,18 +398,21 @@ __global__ void k_syn_from_fft(const uint32_t *__restrict__ res, uint32_t res_st
 //        With acc != nullptr (decode pipeline) the kernel also does k_syn_finish's job: it builds
 //        its syndrome column straight from the bitsliced accumulators (S_2j = S_j^2 through the
 //        tables), writes flag[], and the global syndrome array is never touched.
-// LPC = lanes per codeword (SM only; 2 on the GPU): the two lanes of a pair split the coefficient
-// index by parity -- half the sequential work per codeword, and half the shared memory per thread,
-// so three CTAs are resident instead of two.  Rows are padded by 16 entries so that rows j and j+1
-// of one warp's codewords fall on disjoint banks.
+// LPC = lanes per codeword (SM only; a power of two up to 32): the LPC lanes of a group split the
+// coefficient index j modulo LPC -- 1/LPC of the sequential work per codeword and 1/LPC of the shared
+// memory per thread, so that the (4 d + 3) 16-bit entries per codeword still fit next to the tables when t
+// is large (t = 64: LPC = 8, t = 200: LPC = 16; without that those codes fall back to global scratch and
+// run at L2 latency).  One XOR reduction (discrepancy) and at most one max reduction (degree after
+// cancellation) per iteration go through warp shuffles.  `cs`, the stride between coefficient rows, is
+// padded by the host so that the LPC rows one warp touches fall on disjoint banks.
 template <int M, bool SM, int LPC>
 __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ flag, uint32_t d,
                      uint32_t batch, const uint32_t *__restrict__ gexp, const uint32_t *__restrict__ glog,
                      uint32_t *__restrict__ bm, uint32_t *__restrict__ elp, uint32_t *__restrict__ Lout,
                      const uint32_t *__restrict__ acc, const uint32_t *__restrict__ parity, uint32_t nodd,
-                     uint32_t elp_limit)
+                     uint32_t elp_limit, uint32_t cs_sm)
 {
-  static_assert(LPC == 1 || (LPC == 2 && SM), "lane pairs need the shared-memory variant");
+  static_assert(LPC == 1 || (SM && LPC <= 32 && (LPC & (LPC - 1)) == 0), "lane groups need the shared-memory variant");
   typedef typename std::conditional<SM, uint16_t, uint32_t>::type coef_t;
   const uint32_t order = (1u << M) - 1u;
   BCHFFT_DYN_SMEM(uint16_t, tabs);
@@ -379,29 +420,34 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
   const uint32_t per_cta = blockDim.x / LPC;
   const uint32_t cwl = threadIdx.x / LPC, sub = threadIdx.x % LPC;
   const uint32_t cw = blockIdx.x * per_cta + cwl;
-  const uint32_t pairmask = LPC == 2 ? (3u << (threadIdx.x & 30u)) : 0u;
+  // the LPC lanes of this codeword within the warp
+  const uint32_t pairmask = LPC == 32 ? 0xFFFFFFFFu
+                          : LPC >= 2 ? (((1u << (LPC & 31)) - 1u) << (threadIdx.x & 31u & ~(uint32_t)(LPC - 1))) : 0u;
   auto pair_sync = [&]() {
-#ifndef BCHFFT_EMU
-    if (LPC == 2) __syncwarp(pairmask);
-#endif
+    if (LPC >= 2) __syncwarp(pairmask);
   };
   auto pair_xor = [&](uint32_t v) -> uint32_t {
-#ifndef BCHFFT_EMU
-    if (LPC == 2) v ^= __shfl_xor_sync(pairmask, v, 1);
-#endif
+#pragma unroll
+    for (int o = LPC / 2; o >= 1; o >>= 1) v ^= __shfl_xor_sync(pairmask, v, o);
+    return v;
+  };
+  auto pair_or = [&](uint32_t v) -> uint32_t {
+#pragma unroll
+    for (int o = LPC / 2; o >= 1; o >>= 1) v |= __shfl_xor_sync(pairmask, v, o);
     return v;
   };
   auto pair_max = [&](int v) -> int {
-#ifndef BCHFFT_EMU
-    if (LPC == 2) {
-      const int o = __shfl_xor_sync(pairmask, v, 1);
-      v = o > v ? o : v;
+#pragma unroll
+    for (int o = LPC / 2; o >= 1; o >>= 1) {
+      const int w = __shfl_xor_sync(pairmask, v, o);
+      v = w > v ? w : v;
     }
-#endif
     return v;
   };
-  const size_t cs = SM ? (size_t)(per_cta + (LPC == 2 ? 16u : 0u)) : (size_t)batch;   // stride between coefficients
-  const size_t bs = (size_t)(d + 1) * cs;                                              // stride between buffers
+  // shared-memory indices fit 32 bits (no 64-bit address arithmetic in the recurrence)
+  typedef typename std::conditional<SM, uint32_t, size_t>::type stride_t;
+  const stride_t cs = SM ? (stride_t)cs_sm : (stride_t)batch;   // stride between coefficients
+  const stride_t bs = (stride_t)(d + 1) * cs;                   // stride between buffers
   coef_t *A, *B, *C;
   const coef_t *s;
   uint32_t flagged = 0u;
@@ -419,34 +465,39 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
     s = sc;
     __syncthreads();   // tables complete
     if (acc) {
-      // syndromes from the bitsliced accumulators [slab][nodd][M] (cf. k_syn_finish): first lane
+      // syndromes from the bitsliced accumulators [slab][nodd][M] (cf. k_syn_finish): the lanes of the
+      // group split the odd classes; S_(o 2^e) = S_o^(2^e) follows from the odd one's logarithm
       uint32_t any = 0u;
-      if (cw < batch && sub == 0u) {
+      if (cw < batch) {
         const uint32_t slab = cw >> 5, l = cw & 31u;
-        uint32_t v = (parity[slab] >> l) & 1u;
-        sc[0] = (coef_t)v;
-        any = v;
-        for (uint32_t i = 1; i < d; ++i) {
-          if (i & 1u) {
-            const uint32_t *a = acc + ((size_t)slab * nodd + (i >> 1)) * M;
-            v = 0u;
+        if (sub == 0u) {
+          const uint32_t v = (parity[slab] >> l) & 1u;
+          sc[0] = (coef_t)v;
+          any = v;
+        }
+        // (two loops: the global loads of several classes are in flight together)
+#pragma unroll 4
+        for (uint32_t o = 1u + 2u * sub; o < d; o += 2u * LPC) {
+          const uint32_t *a = acc + ((size_t)slab * nodd + (o >> 1)) * M;
+          uint32_t v = 0u;
 #pragma unroll
-            for (int b = 0; b < M; ++b) v |= ((a[b] >> l) & 1u) << b;
-          } else {
-            const uint32_t h = sc[(i >> 1) * cs];
-            v = 0u;
-            if (h) {
-              uint32_t lg = 2u * (uint32_t)slog[h];
-              if (lg >= order) lg -= order;
-              v = sexp[lg];
-            }
-          }
-          sc[i * cs] = (coef_t)v;
+          for (int b = 0; b < M; ++b) v |= ((a[b] >> l) & 1u) << b;
+          sc[o * cs] = (coef_t)v;
           any |= v;
         }
-        flag[cw] = any ? 1 : 0;
+        for (uint32_t o = 1u + 2u * sub; 2u * o < d; o += 2u * LPC) {
+          const uint32_t v = sc[o * cs];
+          uint32_t lg = v ? (uint32_t)slog[v] : 0u;
+          for (uint32_t i = 2u * o; i < d; i *= 2u) {
+            lg *= 2u;
+            if (lg >= order) lg -= order;
+            sc[i * cs] = (coef_t)(v ? (uint32_t)sexp[lg] : 0u);
+          }
+        }
       }
-      flagged = pair_xor(any ? 1u : 0u);     // the other lane contributes 0
+      any = pair_or(any);
+      if (cw < batch && sub == 0u) flag[cw] = any ? 1 : 0;
+      flagged = any ? 1u : 0u;
     } else {
       for (uint32_t j = sub; j < d; j += LPC) sc[j * cs] = (coef_t)(cw < batch ? syn[(size_t)cw * d + j] : 0u);
       flagged = cw < batch ? (uint32_t)flag[cw] : 0u;
@@ -459,7 +510,7 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
     s = (const coef_t *)syn + (size_t)cw * d;
     flagged = cw < batch ? (uint32_t)flag[cw] : 0u;
   }
-  const size_t ss = SM ? cs : 1;   // stride between syndromes
+  const stride_t ss = SM ? cs : 1;   // stride between syndromes
   auto mul = [&](uint32_t a, uint32_t b) -> uint32_t {
     if (!SM) return gf_mul<M>(a, b);
     if (!a || !b) return 0u;
@@ -860,7 +911,7 @@ k_locate(const uint32_t *__restrict__ F, const uint32_t *__restrict__ counts,
 // group; per tile the K levels run as radix-4 / radix-2 steps, one block per warp, through a
 // [32 positions][M planes][32 lanes] shared-memory buffer (first step reads the forward values,
 // last step feeds the zero test).
-constexpr int kLocUMaxK = 5;
+constexpr int kLocUMaxK = 7;
 // root queue entries per CTA (kernel parameter qcap; BCHFFT_LOCU_QUEUE overrides it so that tests can
 // force the drain and overflow paths; the emulator build defaults to a tiny queue for the same reason)
 #ifdef BCHFFT_EMU
@@ -1044,6 +1095,44 @@ struct LocU {
       store(e3, p0 + 3u * o);
     }
   }
+  // BF(d), BF(d-1) for d = 5, 6 (first step of the buckets K = d + 1 = 6, 7): the radix-4 group
+  // {i, i+o, i+2o, i+3o}, o = 2^(d-1), spans 2 or 4 tiles.  Its inputs are forward values, which every
+  // tile can read, so a tile recomputes the part of the group that ends in it: both products of level
+  // d, then one butterfly of level d-1 -- 3 multiplies for 2 outputs (d = 5: local positions i, i+16)
+  // or for 1 output (d = 6: local position i) instead of 4 multiplies for 4 outputs.
+  __device__ __forceinline__ void radix4_wide(uint32_t d, uint32_t i) const
+  {
+    const uint32_t o = 1u << (d - 1u);
+    const uint32_t r0 = tile0 & kmask;          // first position of this tile within its 2^(d+1) block
+    const uint32_t hi = r0 >> d;                // the tile lies in the upper half of level d
+    uint32_t e0[M], e1[M], e2[M], e3[M];
+    load(e0, i, true);
+    load(e1, i + o, true);
+    load(e2, i + 2u * o, true);
+    load(e3, i + 3u * o, true);
+    const uint32_t q = tile0 >> (d + 1u);
+    const uint32_t G = gam[gam_off[d] + q];
+    if (G) bs_mad_uniform2<M>(e0, e2, e1, e3, G);
+    if (hi) {
+#pragma unroll
+      for (int b = 0; b < M; ++b) {
+        e0[b] ^= e2[b];
+        e1[b] ^= e3[b];
+      }
+    }
+    const uint32_t Gx = gam[gam_off[d - 1u] + 2u * q + hi];
+    if (Gx) bs_mad_uniform<M>(e0, e1, Gx);
+#pragma unroll
+    for (int b = 0; b < M; ++b) e1[b] ^= e0[b];
+    if (d == 5u) {
+      store(e0, i);
+      store(e1, i + 16u);
+    } else if ((r0 >> 5) & 1u) {
+      store(e1, i);
+    } else {
+      store(e0, i);
+    }
+  }
   // BF(0) on pair pw (0..15) of the tile; always the last step
   __device__ __forceinline__ void radix2_last(uint32_t pw, bool from_f) const
   {
@@ -1124,7 +1213,12 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
     for (uint32_t s = 0; s < nsteps; ++s) {
       const uint32_t d = K - 1u - 2u * s;
       const bool from_f = s == 0u, last = s + 1u == nsteps;
-      if (d >= 1u) {
+      if (d >= 5u) {
+        // K = 6, 7: groups that span several tiles (first step only)
+        const uint32_t ng = d == 5u ? 16u : 32u;
+#pragma unroll 1
+        for (uint32_t b = warp; b < ng; b += nwarps) job.radix4_wide(d, b);
+      } else if (d >= 1u) {
 #pragma unroll 1
         for (uint32_t b = 0; b < 8u; ++b)
           if ((b & (nwarps - 1u)) == warp) job.radix4(d, b, from_f, last);

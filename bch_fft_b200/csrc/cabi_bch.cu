@@ -160,7 +160,7 @@ static int launch_syndrome(bchfft_code *c, bchfft_code::WorkSet &w, const uint64
   }
   const char *penv = getenv("BCHFFT_SYN_P");
   if (c->syn_p && !(penv && atoi(penv) == 0)) {
-    const size_t smem_p = 2u * sizeof(uint32_t) * ((size_t)((c->f->order + 31u) / 32u) * 33u + (size_t)c->nodd * M);
+    const size_t smem_p = 2u * sizeof(uint32_t) * ((size_t)((c->f->order + 31u) / 32u) * 32u + (size_t)c->nodd * M);
     BCHFFT_ENSURE_SMEM(k_syndrome_p<M>, c->f->device, smem_p);
     BCHFFT_RUN(k_syndrome_p<M>, dim3((ns + 1u) / 2u), dim3(kNtSyn), smem_p, st, (const uint32_t *)d_words, c->wpc * 2u,
                c->length, (uint32_t)cnt, c->nodd, (const uint32_t *)c->d_lcs, (const uint32_t *)c->d_jinv,
@@ -186,13 +186,8 @@ static int launch_syndrome(bchfft_code *c, bchfft_code::WorkSet &w, const uint64
 
 #ifdef BCHFFT_EMU
 static const unsigned kBmThreads = 32;
-static constexpr int kBmLpc = 1;      // the emulator has no warp shuffles
 #else
 static const unsigned kBmThreads = 256;
-#ifndef BCHFFT_BM_LPC
-#define BCHFFT_BM_LPC 1   /* measured: lane pairs (2) are slower, 1.12 ms against 1.02 ms */
-#endif
-static constexpr int kBmLpc = BCHFFT_BM_LPC;      // lanes per codeword of the shared-memory kernel
 #endif
 
 // Few codewords with a long recurrence (single decode at n = 65535, t = 1000): one CTA per codeword
@@ -204,17 +199,83 @@ static bool bm_wide(const bchfft_code *c, size_t cnt)
   return c->t >= 24u && cnt <= (size_t)16 * c->t && smem_w <= (size_t)200 * 1024 && !(wenv && atoi(wenv) == 0);
 }
 
-// true when launch_bm takes the shared-memory kernel, which can also finish the syndromes itself
-template <int M>
-static bool bm_in_smem(const bchfft_code *c, unsigned *nt_out, size_t *smem_out)
+// Launch shape of the shared-memory Berlekamp-Massey kernel: lanes per codeword (lpc), threads, stride
+// between coefficient rows (cs, 16-bit entries) and dynamic shared memory.
+struct BmShape {
+  unsigned lpc, nt, cs;
+  size_t smem;
+};
+
+// One thread per codeword while (4 d + 3) 16-bit entries per thread fit next to the log / exp tables
+// (measured at t = 16: lane pairs are slower, 1.12 ms against 1.02 ms); for larger d the smallest lane
+// group (4, 8, 16, 32 lanes) that leaves room for three CTAs per SM.  Measured, k_bm per 262144 words at
+// t = 64: 4 lanes 3.8 ms, 8 lanes 3.5 ms (the rule's choice), 16 lanes 4.0 ms, global scratch 6.8 ms; per
+// 131072 words at t = 200: 8 lanes 28 ms, 16 lanes 17.7 ms, 32 lanes 15.9 ms (the rule's choice), global
+// scratch 36 ms.  BCHFFT_BM_LPC forces a group size.
+// The stride between coefficient rows is the smallest one for which the rows j, j+1, .. j+lpc-1 that
+// one warp touches in one access fall on disjoint banks.  false: the code takes the global-scratch kernel.
+static unsigned bm_row_stride(unsigned per_cta, unsigned lpc)
 {
-  const unsigned nt = kBmThreads;
-  const size_t cs = nt / kBmLpc + (kBmLpc == 2 ? 16u : 0u);
-  const size_t smem = sizeof(uint16_t) * (((size_t)2 << M) + (size_t)(4 * c->d + 3) * cs);
+  unsigned cs = (per_cta + 1u) & ~1u;
+  if (lpc == 1u) return per_cta;
+  for (; cs < per_cta + 160u; cs += 2u) {
+    uint32_t word_of_bank[32];
+    bool used[32] = {false}, clash = false;
+    for (unsigned lane = 0; lane < 32u && !clash; lane++) {
+      const unsigned sub = lane % lpc, g = lane / lpc;
+      const uint32_t word = (sub * cs + g) >> 1, bank = word & 31u;
+      if (used[bank] && word_of_bank[bank] != word) clash = true;
+      used[bank] = true;
+      word_of_bank[bank] = word;
+    }
+    if (!clash) return cs;
+  }
+  return (per_cta + 1u) & ~1u;
+}
+
+template <int M>
+static bool bm_in_smem(const bchfft_code *c, BmShape *out)
+{
   const char *benv = getenv("BCHFFT_BM_SM");
-  *nt_out = nt;
-  *smem_out = smem;
-  return M <= 14 && smem <= (size_t)110 * 1024 && !(benv && atoi(benv) == 0);
+  if (M > 14 || (benv && atoi(benv) == 0)) return false;
+  const unsigned nt = kBmThreads;
+  const char *lenv = getenv("BCHFFT_BM_LPC");
+  const unsigned forced = lenv ? (unsigned)atoi(lenv) : 0u;
+  // shared memory per CTA the shape may take: a lane group wants three CTAs per SM; when no group size
+  // gets there, two CTAs or a single one still beat the global-scratch kernel
+  const unsigned options[6] = {1u, 2u, 4u, 8u, 16u, 32u};
+  const size_t limits[3] = {(size_t)75 * 1024, (size_t)110 * 1024, (size_t)200 * 1024};
+  for (unsigned round = 0; round < 3; round++)
+    for (unsigned k = 0; k < 6; k++) {
+      const unsigned lpc = options[k];
+      if (forced ? lpc != forced : lpc == 2u) continue;
+      if (lpc > nt) break;
+      const unsigned cs = bm_row_stride(nt / lpc, lpc);
+      const size_t smem = sizeof(uint16_t) * (((size_t)2 << M) + (size_t)(4 * c->d + 3) * cs);
+      const size_t limit = (lpc == 1u && round == 0) ? limits[1] : limits[round];
+      if (smem <= limit) {
+        out->lpc = lpc;
+        out->nt = nt;
+        out->cs = cs;
+        out->smem = smem;
+        return true;
+      }
+    }
+  return false;
+}
+
+template <int M, int LPC>
+static int launch_bm_sm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t st, bool fused, uint32_t elp_limit,
+                        const BmShape &b)
+{
+  const unsigned per_cta = b.nt / LPC;
+  BCHFFT_ENSURE_SMEM((k_bm<M, true, LPC>), c->f->device, b.smem);
+  BCHFFT_RUN((k_bm<M, true, LPC>), dim3((unsigned)((cnt + per_cta - 1) / per_cta)), dim3(b.nt), b.smem, st,
+             (const uint32_t *)s.syn, s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
+             (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L,
+             fused ? (const uint32_t *)s.acc : (const uint32_t *)nullptr, (const uint32_t *)s.parity, c->nodd,
+             elp_limit, (uint32_t)b.cs);
+  return BCHFFT_OK;
 }
 
 // fused: the syndromes are still bitsliced accumulators (launch_syndrome(..., finish = false));
@@ -223,8 +284,6 @@ template <int M>
 static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t st, bool fused = false,
                      uint32_t elp_limit = 0xFFFFFFFFu)
 {
-  unsigned nt;
-  size_t smem;
   if (!fused && bm_wide(c, cnt)) {
     const size_t smem_w = sizeof(uint32_t) * ((size_t)4 * c->d + 3u);
     unsigned ntw = ((c->t + 1u + 31u) / 32u) * 32u;
@@ -235,26 +294,27 @@ static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t 
                (const uint32_t *)c->f->d_log, s.elp, s.L, elp_limit);
     return BCHFFT_OK;
   }
-  if (bm_in_smem<M>(c, &nt, &smem)) {
-    constexpr bool kSm = M <= 14;
-    constexpr int kLpc = kSm ? kBmLpc : 1;
-    const unsigned per_cta = nt / kLpc;
-    BCHFFT_ENSURE_SMEM((k_bm<M, kSm, kLpc>), c->f->device, smem);
-    BCHFFT_RUN((k_bm<M, kSm, kLpc>), dim3((unsigned)((cnt + per_cta - 1) / per_cta)), dim3(nt), smem, st,
-               (const uint32_t *)s.syn, s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
-               (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L,
-               fused ? (const uint32_t *)s.acc : (const uint32_t *)nullptr, (const uint32_t *)s.parity, c->nodd,
-               elp_limit);
-  } else {
-    if (fused) {
-      set_error("bch decode: internal error (fused Berlekamp-Massey without the shared-memory kernel)");
-      return BCHFFT_ERR_ARG;
+  BmShape b;
+  if constexpr (M <= 14) {
+    if (bm_in_smem<M>(c, &b)) {
+      switch (b.lpc) {
+        case 1: return launch_bm_sm<M, 1>(c, cnt, s, st, fused, elp_limit, b);
+        case 2: return launch_bm_sm<M, 2>(c, cnt, s, st, fused, elp_limit, b);
+        case 4: return launch_bm_sm<M, 4>(c, cnt, s, st, fused, elp_limit, b);
+        case 8: return launch_bm_sm<M, 8>(c, cnt, s, st, fused, elp_limit, b);
+        case 16: return launch_bm_sm<M, 16>(c, cnt, s, st, fused, elp_limit, b);
+        default: return launch_bm_sm<M, 32>(c, cnt, s, st, fused, elp_limit, b);
+      }
     }
-    BCHFFT_RUN((k_bm<M, false, 1>), dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
-               (const uint32_t *)s.syn, s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
-               (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L, (const uint32_t *)nullptr,
-               (const uint32_t *)nullptr, 0u, elp_limit);
   }
+  if (fused) {
+    set_error("bch decode: internal error (fused Berlekamp-Massey without the shared-memory kernel)");
+    return BCHFFT_ERR_ARG;
+  }
+  BCHFFT_RUN((k_bm<M, false, 1>), dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
+             (const uint32_t *)s.syn, s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
+             (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L, (const uint32_t *)nullptr,
+             (const uint32_t *)nullptr, 0u, elp_limit, 0u);
   return BCHFFT_OK;
 }
 
@@ -317,7 +377,8 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
     {
       const size_t smem_f = sizeof(uint32_t) * M * 256u;
       BCHFFT_ENSURE_SMEM(k_elp_fwd_u<M>, c->f->device, smem_f);
-      BCHFFT_RUN(k_elp_fwd_u<M>, dim3((ns + 7u) >> 3, (unsigned)kmax), dim3(256), smem_f, st,
+      const unsigned sb_min = kmax >= 5 ? 8u - (unsigned)kmax : 3u;       // slabs per CTA of the largest bucket: 2^sb_min
+      BCHFFT_RUN(k_elp_fwd_u<M>, dim3((ns + (1u << sb_min) - 1u) >> sb_min, (unsigned)kmax), dim3(256), smem_f, st,
                  (const uint32_t *)s.elp, (const uint32_t *)s.L, c->d, (const uint32_t *)counts,
                  (const uint32_t *)lists, (uint32_t)cnt, (uint32_t)kmax, c->f->tab,
                  (const PassDesc *)(d_descs + (kMaxBuckets + 1)), F);
@@ -383,10 +444,9 @@ static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words
     carve(c, w.scratch.p, cnt, pos_stride, M, s);
     uint64_t *wp = d_words + i0 * c->wpc;
     // the shared-memory Berlekamp-Massey kernel un-bitslices the syndromes itself
-    unsigned nt_bm;
-    size_t smem_bm;
+    BmShape bm_shape;
     const char *fenv = getenv("BCHFFT_BM_FUSED");
-    const bool bm_sm = bm_in_smem<M>(c, &nt_bm, &smem_bm);
+    const bool bm_sm = bm_in_smem<M>(c, &bm_shape);
     const bool fused = bm_sm && !bm_wide(c, cnt) && !(fenv && atoi(fenv) == 0);
     BCHFFT_CUDA_TRY(cudaMemsetAsync(w.scratch.p, 0, zero_bytes(c, cnt, M, !bm_sm), st));
     if ((rc = launch_syndrome<M>(c, w, wp, cnt, s, st, !fused))) return rc;
@@ -545,7 +605,7 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
     auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t r = a % b; a = b; b = r; } return a; };
     bool ok = M >= 9 && M <= 15 && length <= order;
     for (uint32_t ji = 0; ji < c->nodd && ok; ji++) ok = gcd((2u * ji + 1u) % order, order) == 1u;
-    const size_t smem_p = 2u * sizeof(uint32_t) * ((size_t)((order + 31u) / 32u) * 33u + (size_t)c->nodd * M);
+    const size_t smem_p = 2u * sizeof(uint32_t) * ((size_t)((order + 31u) / 32u) * 32u + (size_t)c->nodd * M);
     if (ok && smem_p <= (size_t)200 * 1024) {
       const uint32_t lc_min = (order + 31u) / 32u, lc_max = lc_min + lc_min / 8u;
       auto inverse = [&](uint32_t v) -> uint32_t {   // v^-1 mod order by the extended Euclid
@@ -572,7 +632,7 @@ extern "C" int bchfft_code_create(bchfft_field *f, uint32_t distance, uint32_t l
             uint32_t worst = 0;
             for (uint32_t q = half * 16u; q < half * 16u + 16u; q++) {
               if (k >= n[q]) continue;
-              const uint32_t bank = (idx[q] + (idx[q] >> 5)) & 15u;
+              const uint32_t bank = idx[q] & 15u;
               if (++load[bank] > worst) worst = load[bank];
               idx[q] = idx[q] >= step4 ? idx[q] - step4 : idx[q] + order - step4;
             }

@@ -176,6 +176,43 @@ def test_emu_bch_stages_and_decode_vs_oracle(emu_libs, port, n, t):
     cabi.bchfft_field_destroy(h)
 
 
+@pytest.mark.parametrize("lpc", [2, 4, 8, 16, 32])
+@pytest.mark.parametrize("n,t", [(255, 20), (8191, 16), (8191, 64), (1023, 10)])
+def test_emu_berlekamp_massey_lane_groups(emu_libs, port, monkeypatch, n, t, lpc):
+    """k_bm with `lpc` lanes per codeword (the shape large-t codes take on the GPU so that the
+    coefficient buffers stay in shared memory), forced through BCHFFT_BM_LPC: stage-level call
+    (syndromes from the array) and fused decode (syndromes from the bitsliced accumulators)"""
+    monkeypatch.setenv("BCHFFT_BM_LPC", str(lpc))
+    monkeypatch.setenv("BCHFFT_BM_WIDE", "0")      # few codewords with t >= 24 would take k_bm_wide
+    cabi, _ = emu_libs
+    pc = port.code(n, t)
+    h = _field(cabi, port, pc.m)
+    c = C.c_void_p()
+    _lib.check(cabi, cabi.bchfft_code_create(h, 2 * t + 1, n, pc.gen.ctypes.data, pc.gen_degree,
+                                             C.byref(c)), "code")
+    B, d = 37, 2 * t + 1
+    words = _words_for(pc, n, t, B, np.random.default_rng(n + t + lpc))
+    syn = np.zeros((B, d), np.uint32)
+    flags = np.zeros(B, np.int32)
+    _lib.check(cabi, cabi.bchfft_bch_syndrome_host(c, words.ctypes.data, B, syn.ctypes.data,
+                                                   flags.ctypes.data), "syndrome")
+    elp = np.zeros((B, d + 1), np.uint32)
+    L = np.zeros(B, np.uint32)
+    _lib.check(cabi, cabi.bchfft_bch_elp_host(c, syn.ctypes.data, B, elp.ctypes.data, L.ctypes.data), "elp")
+    for b in range(B):
+        Lr, er = pc.elp(syn[b])
+        assert L[b] == Lr and (elp[b, : Lr + 1] == er).all(), (b, L[b], Lr)
+    ok = np.zeros(B, np.uint8)
+    corr = np.zeros(B, np.uint32)
+    out = words.copy()
+    _lib.check(cabi, cabi.bchfft_bch_decode_host(c, out.ctypes.data, B, ok.ctypes.data,
+                                                 corr.ctypes.data), "decode")
+    rok, rcorr, rw = pc.decode_batch(words)
+    assert (ok == rok).all() and (corr == rcorr).all() and (out == rw).all()
+    cabi.bchfft_code_destroy(c)
+    cabi.bchfft_field_destroy(h)
+
+
 @pytest.mark.parametrize("rec", [r for r in GOLDEN["decode"] if r["n"] <= 8191 and r["t"] <= 64],
                          ids=lambda r: f"n{r['n']}-t{r['t']}")
 def test_emu_host_api_decode_golden(emu_libs, rec):

@@ -145,6 +145,46 @@ __device__ __forceinline__ void mad_variant(uint32_t (&acc)[M], const uint32_t (
   bs_reduce<M>(q);
 #pragma unroll
   for (int i = 0; i < M; ++i) acc[i] = q[i];
+#elif MB_VARIANT == 7
+  // warp-uniform constant, two bits of c per branch, running multiple t = a x^j kept reduced:
+  // no double-width accumulator, no final reduction, no register moves (the names rotate statically)
+  constexpr uint32_t taps = field_poly(M) & ((1u << M) - 1u);
+  uint32_t t[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) t[i] = a[i];
+#pragma unroll
+  for (int j = 0; j < M; j += 2) {
+    const uint32_t two = (c >> j) & 3u;
+    // tx = t x
+    uint32_t tx[M];
+    {
+      const uint32_t top = t[M - 1];
+#pragma unroll
+      for (int i = M - 1; i >= 1; --i) tx[i] = ((taps >> i) & 1u) ? (t[i - 1] ^ top) : t[i - 1];
+      tx[0] = top;
+    }
+    if (j + 1 == M) {
+      if (two & 1u) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) acc[i] ^= t[i];
+      }
+    } else if (two == 1u) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) acc[i] ^= t[i];
+    } else if (two == 2u) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) acc[i] ^= tx[i];
+    } else if (two == 3u) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) acc[i] = xor3(acc[i], t[i], tx[i]);
+    }
+    if (j + 2 < M) {
+      const uint32_t top = tx[M - 1];
+#pragma unroll
+      for (int i = M - 1; i >= 1; --i) t[i] = ((taps >> i) & 1u) ? (tx[i - 1] ^ top) : tx[i - 1];
+      t[0] = top;
+    }
+  }
 #elif MB_VARIANT == 5
   // warp-uniform constant, predication instead of branches: one predicate per bit of c guards the
   // M XORs of that bit (one asm block each, so that ptxas keeps them predicated)

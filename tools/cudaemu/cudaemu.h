@@ -11,8 +11,8 @@
 // Supported: __global__/__device__/__shared__ (static and dynamic), threadIdx/blockIdx/
 // blockDim/gridDim, __syncthreads, atomicAdd/atomicXor/atomicOr (trivially atomic: fibers are
 // cooperative), __popc/__ffs/__brev/__clz, and the slice of the runtime API the C-ABI layer
-// uses (malloc/free/memcpy/memset/streams/events as no-ops).  Not supported: warp shuffles,
-// votes, cooperative groups, textures.
+// uses (malloc/free/memcpy/memset/streams/events as no-ops), __shfl_xor_sync between lanes that run in
+// lock step.  Not supported: other shuffles, votes, cooperative groups, textures.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -50,6 +50,7 @@ struct Fiber {
   uint3 tid;
   bool done;
   char *stack;
+  unsigned shfl_phase;   // parity of this thread's next emulated warp shuffle
 };
 struct State {
   ucontext_t sched;
@@ -97,6 +98,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, Body body)
               Fiber &f = fibers[k];
               f.tid = uint3{tx, ty, tz};
               f.done = false;
+              f.shfl_phase = 0u;
               getcontext(&f.ctx);
               f.ctx.uc_stack.ss_sp = f.stack;
               f.ctx.uc_stack.ss_size = stack_bytes;
@@ -133,6 +135,27 @@ static inline void __syncthreads()
 // kernels whose warps all reach the same number of barriers)
 static inline void __syncwarp(unsigned = 0xffffffffu) { __syncthreads(); }
 static inline void __threadfence() {}
+// Warp shuffle among lanes that run in lock step (the same sequence of yields, e.g. the lane group of
+// one codeword in k_bm): every lane posts its value, yields once, and reads the partner's post.  Two
+// post buffers alternate, because a lower-numbered lane resumes first and may already have posted
+// its next value by the time the partner reads this one.
+namespace cudaemu {
+inline uint32_t *shfl_post() { static thread_local uint32_t post[2][1024]; return &post[0][0]; }
+}
+static inline uint32_t __shfl_xor_sync(unsigned, uint32_t v, int lane_mask)
+{
+  cudaemu::State &s = cudaemu::st();
+  const unsigned me = s.cur->tid.x, ph = s.cur->shfl_phase;
+  s.cur->shfl_phase = ph ^ 1u;
+  uint32_t *post = cudaemu::shfl_post() + ph * 1024u;
+  post[me] = v;
+  __syncthreads();
+  return post[me ^ (unsigned)lane_mask];
+}
+static inline int __shfl_xor_sync(unsigned m, int v, int lane_mask)
+{
+  return (int)__shfl_xor_sync(m, (uint32_t)v, lane_mask);
+}
 
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> static inline T atomicXor(T *p, T v) { T o = *p; *p = o ^ v; return o; }
