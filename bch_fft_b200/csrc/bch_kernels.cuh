@@ -749,27 +749,117 @@ __device__ __forceinline__ uint32_t locator_bucket(uint32_t L)   // ceil(log2(L 
   return 32u - (uint32_t)__clz((int)L);
 }
 
-// counts: [kMaxBuckets + 1] zero-initialised; lists: [kMaxBuckets + 1][batch] codeword indices.
-// Codewords with nothing to locate (not flagged, L = 0: constant locator, or L > tcap) stay out.
-__global__ void k_bucket(const int32_t *__restrict__ flag, const uint32_t *__restrict__ Lin,
-                         uint32_t tcap, uint32_t batch, uint32_t *__restrict__ counts,
-                         uint32_t *__restrict__ lists)
+// Closed-form roots of a locator of degree <= 2 (C[0] = 1): 1 + c1 x has the root 1 / c1;
+// 1 + c1 x + c2 x^2 with c1, c2 != 0 becomes y^2 + y = u = c2 / c1^2 under x = (c1 / c2) y, which has
+// the solutions y0, y0 + 1 exactly when Tr(u) = 0, y0 = sum over the set bits k of u of h_k with
+// h_k^2 + h_k = x^k (+ a fixed trace-one element when Tr(x^k) = 1; those cancel in pairs);
+// c1 = 0: the double root sqrt(1 / c2) is one point.  qs = {trace mask, h_0 .. h_(m-1)}.  Reports what
+// the exhaustive search would: a root x^i counts as position order - i (bch.c:479-488).
+// Returns the number of roots.
+__device__ __forceinline__ uint32_t locator_roots_direct(uint32_t L, uint32_t c1, uint32_t c2, uint32_t order,
+                                                         const uint32_t *__restrict__ glog,
+                                                         const uint32_t *__restrict__ gexp,
+                                                         const uint32_t *__restrict__ qs, uint32_t (&where)[2])
 {
-  __shared__ uint32_t hist[kMaxBuckets + 1], base[kMaxBuckets + 1];
-  if (threadIdx.x <= kMaxBuckets) hist[threadIdx.x] = 0u;
+  if (L < 2u) c2 = 0u;
+  if (!c2) {
+    if (!c1) return 0u;
+    where[0] = order - (order - glog[c1]) % order;          // log(1 / c1) = (order - log c1) mod order
+    return 1u;
+  }
+  const uint32_t l2 = glog[c2];
+  if (!c1) {
+    // x^2 = 1 / c2: halve the logarithm (2^-1 = (order + 1) / 2 mod order)
+    const uint32_t lg = (uint32_t)(((uint64_t)((order - l2) % order) * ((order + 1u) / 2u)) % order);
+    where[0] = order - lg;
+    return 1u;
+  }
+  const uint32_t l1 = glog[c1];
+  const uint32_t u = gexp[(l2 + 2u * (order - l1)) % order];
+  if (__popc(u & qs[0]) & 1u) return 0u;                     // Tr(u) = 1: no root in the field
+  uint32_t y0 = 0u;
+  for (uint32_t k = 0, v = u; v; ++k, v >>= 1)
+    if (v & 1u) y0 ^= qs[1u + k];
+  const uint32_t lr = (l1 + order - l2) % order;             // log(c1 / c2)
+  const uint32_t la = (lr + glog[y0]) % order, lb = (lr + glog[y0 ^ 1u]) % order;
+  where[0] = order - la;
+  where[1] = order - lb;
+  return 2u;
+}
+
+// Counting sort of the codewords that need a root search, by locator degree L: bucket K =
+// ceil(log2(L + 1)) holds its codewords in ascending L, so that the 1024 codewords of a slab group
+// have (almost) the same degree and k_locate_u can skip the forward values that are zero for the whole
+// group (coefficient i of the converted locator vanishes for i > L).
+//   counts:  [kMaxBuckets + 1] codewords per bucket (written by k_bucket_scatter)
+//   by_deg:  [2][tcap + 1] zero-initialised: codewords per degree, scatter cursors per degree
+//   lists:   [kMaxBuckets + 1][batch] codeword indices
+// Codewords with nothing to locate (not flagged, L = 0: constant locator, or L > tcap) stay out.
+// direct_max (0, 1 or 2): locators of degree <= direct_max are solved in closed form by k_bucket_count
+// (count[] and positions[] written) and stay out of the buckets as well.
+// Both kernels: dynamic smem = 2 (tcap + 1) words, same grid.
+__global__ void k_bucket_count(const int32_t *__restrict__ flag, const uint32_t *__restrict__ Lin,
+                               uint32_t tcap, uint32_t batch, uint32_t *__restrict__ by_deg, uint32_t direct_max,
+                               const uint32_t *__restrict__ elp, uint32_t d, uint32_t order,
+                               const uint32_t *__restrict__ glog, const uint32_t *__restrict__ gexp,
+                               const uint32_t *__restrict__ qs, uint32_t *__restrict__ count,
+                               uint32_t *__restrict__ positions, uint32_t pos_stride)
+{
+  BCHFFT_DYN_SMEM(uint32_t, hist);
+  for (uint32_t i = threadIdx.x; i <= tcap; i += blockDim.x) hist[i] = 0u;
   __syncthreads();
   const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t b = 0u, rank = 0u;
   if (cw < batch && flag[cw]) {
     const uint32_t L = Lin[cw];
-    if (L >= 1u && L <= tcap) b = locator_bucket(L);
+    if (L >= 1u && L <= tcap) {
+      if (L <= direct_max) {
+        const uint32_t *e = elp + (size_t)cw * (d + 1);
+        uint32_t where[2];
+        const uint32_t nr = locator_roots_direct(L, e[1], L >= 2u ? e[2] : 0u, order, glog, gexp, qs, where);
+        for (uint32_t k = 0; k < nr && k < pos_stride; ++k) positions[(size_t)cw * pos_stride + k] = where[k];
+        count[cw] = nr;
+      } else {
+        atomicAdd(&hist[L], 1u);
+      }
+    }
   }
-  if (b) rank = atomicAdd(&hist[b], 1u);
   __syncthreads();
-  if (threadIdx.x >= 1 && threadIdx.x <= kMaxBuckets && hist[threadIdx.x])
-    base[threadIdx.x] = atomicAdd(&counts[threadIdx.x], hist[threadIdx.x]);
+  for (uint32_t i = threadIdx.x; i <= tcap; i += blockDim.x)
+    if (hist[i]) atomicAdd(&by_deg[i], hist[i]);
+}
+
+__global__ void k_bucket_scatter(const int32_t *__restrict__ flag, const uint32_t *__restrict__ Lin,
+                                 uint32_t tcap, uint32_t batch, uint32_t *__restrict__ counts,
+                                 uint32_t *__restrict__ by_deg, uint32_t *__restrict__ lists, uint32_t direct_max)
+{
+  BCHFFT_DYN_SMEM(uint32_t, sm);
+  uint32_t *hist = sm, *start = sm + (tcap + 1u);      // per degree: codewords of this CTA, first list slot
+  const uint32_t *per_deg = by_deg;
+  uint32_t *cursor = by_deg + (tcap + 1u);
+  for (uint32_t i = threadIdx.x; i <= tcap; i += blockDim.x) hist[i] = 0u;
   __syncthreads();
-  if (b) lists[(size_t)b * batch + base[b] + rank] = cw;
+  const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t L = 0u, rank = 0u;
+  if (cw < batch && flag[cw]) {
+    const uint32_t l = Lin[cw];
+    if (l > direct_max && l >= 1u && l <= tcap) {
+      L = l;
+      rank = atomicAdd(&hist[L], 1u);
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i <= tcap; i += blockDim.x) {
+    if (!i) continue;
+    // degrees below i in the same bucket come first
+    const uint32_t lowest = 1u << (locator_bucket(i) - 1u);
+    uint32_t before = 0u;
+    for (uint32_t j = lowest; j < i; ++j) before += per_deg[j];
+    if (blockIdx.x == 0u && (i == tcap || locator_bucket(i + 1u) != locator_bucket(i)))
+      counts[locator_bucket(i)] = before + per_deg[i];
+    start[i] = hist[i] ? before + atomicAdd(&cursor[i], hist[i]) : 0u;
+  }
+  __syncthreads();
+  if (L) lists[(size_t)locator_bucket(L) * batch + start[L] + rank] = cw;
 }
 
 // Forward phase for bucket K = fwd.dom_bits.  grid = worst-case number of slab groups (CTAs
@@ -1014,6 +1104,7 @@ struct LocU {
   const uint32_t *glist, *errloc;   // overflow path: the group's codeword list, position table
   uint32_t *count, *positions;
   uint32_t active, kmask, tile0, lane, pos_stride, qcap;
+  uint32_t lmax;              // largest locator degree of the group: forward values above it are zero
 
   __device__ __forceinline__ void load(uint32_t (&e)[M], uint32_t p, bool from_f) const
   {
@@ -1063,13 +1154,29 @@ struct LocU {
     const uint32_t p0 = ((bw >> lb) << (lb + 2u)) | (bw & ((1u << lb) - 1u));
     const uint32_t o = 1u << lb;
     uint32_t e0[M], e1[M], e2[M], e3[M];
+    // first step: the upper half of the forward values is zero above the group's largest degree
+    // (the codewords of a bucket are sorted by degree) -- nothing to load, nothing to multiply
+    const bool z2 = from_f && ((p0 + 2u * o) & kmask) > lmax, z3 = from_f && ((p0 + 3u * o) & kmask) > lmax;
     load(e0, p0, from_f);
     load(e1, p0 + o, from_f);
-    load(e2, p0 + 2u * o, from_f);
-    load(e3, p0 + 3u * o, from_f);
+    if (z2) {
+#pragma unroll
+      for (int b = 0; b < M; ++b) e2[b] = 0u;
+    } else {
+      load(e2, p0 + 2u * o, from_f);
+    }
+    if (z3) {
+#pragma unroll
+      for (int b = 0; b < M; ++b) e3[b] = 0u;
+    } else {
+      load(e3, p0 + 3u * o, from_f);
+    }
     const uint32_t gp = tile0 + p0;
     const uint32_t G = gam[gam_off[d] + (gp >> (d + 1u))];
-    if (G) bs_mad_uniform2<M>(e0, e2, e1, e3, G);
+    if (G) {
+      if (!z3) bs_mad_uniform2<M>(e0, e2, e1, e3, G);
+      else if (!z2) bs_mad_uniform<M>(e0, e2, G);
+    }
 #pragma unroll
     for (int b = 0; b < M; ++b) {
       e2[b] ^= e0[b];
@@ -1106,13 +1213,27 @@ struct LocU {
     const uint32_t r0 = tile0 & kmask;          // first position of this tile within its 2^(d+1) block
     const uint32_t hi = r0 >> d;                // the tile lies in the upper half of level d
     uint32_t e0[M], e1[M], e2[M], e3[M];
+    const bool z2 = i + 2u * o > lmax, z3 = i + 3u * o > lmax;   // see radix4
     load(e0, i, true);
     load(e1, i + o, true);
-    load(e2, i + 2u * o, true);
-    load(e3, i + 3u * o, true);
+    if (z2) {
+#pragma unroll
+      for (int b = 0; b < M; ++b) e2[b] = 0u;
+    } else {
+      load(e2, i + 2u * o, true);
+    }
+    if (z3) {
+#pragma unroll
+      for (int b = 0; b < M; ++b) e3[b] = 0u;
+    } else {
+      load(e3, i + 3u * o, true);
+    }
     const uint32_t q = tile0 >> (d + 1u);
     const uint32_t G = gam[gam_off[d] + q];
-    if (G) bs_mad_uniform2<M>(e0, e2, e1, e3, G);
+    if (G) {
+      if (!z3) bs_mad_uniform2<M>(e0, e2, e1, e3, G);
+      else if (!z2) bs_mad_uniform<M>(e0, e2, G);
+    }
     if (hi) {
 #pragma unroll
       for (int b = 0; b < M; ++b) {
@@ -1154,7 +1275,8 @@ struct LocU {
 template <int M>
 __global__ void __launch_bounds__(BCHFFT_NT_LOC, BCHFFT_MINB_LOCU)
 k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
-           const uint32_t *__restrict__ lists, uint32_t batch, uint32_t kmax, FftTables tab,
+           const uint32_t *__restrict__ lists, const uint32_t *__restrict__ Lin, uint32_t batch, uint32_t kmax,
+           FftTables tab,
            const uint32_t *__restrict__ errloc, uint32_t *__restrict__ count,
            uint32_t *__restrict__ positions, uint32_t pos_stride, uint32_t qcap)
 {
@@ -1192,6 +1314,11 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
   job.pos_stride = pos_stride;
   job.qcap = qcap;
   job.active = first >= pop ? 0u : (pop - first >= 32u ? 0xFFFFFFFFu : ((1u << (pop - first)) - 1u));
+  {
+    // the bucket's list ascends in degree: the group's last codeword has its largest one
+    const uint32_t gfirst = v * 1024u, gend = pop - gfirst < 1024u ? pop : gfirst + 1024u;
+    job.lmax = Lin ? Lin[glist[gend - 1u - gfirst]] : 0xFFFFFFFFu;
+  }
   const uint32_t nsteps = (K + 1u) >> 1;
   const uint32_t ntiles = (1u << M) >> 5;
   const uint32_t per = (ntiles + gridDim.x - 1u) / gridDim.x;

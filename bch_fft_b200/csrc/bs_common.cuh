@@ -60,6 +60,11 @@
 #ifndef BCHFFT_UNI_BF
 #define BCHFFT_UNI_BF 1
 #endif
+// radix-4 sweeps of the FFT pass kernels: the two butterflies that share a multiplier in one branch
+// sequence (bs_mad_uniform2; more registers live at once)
+#ifndef BCHFFT_R4_MAD2
+#define BCHFFT_R4_MAD2 0
+#endif
 #ifndef BCHFFT_MINB_SYNP
 #define BCHFFT_MINB_SYNP 3
 #endif

@@ -346,14 +346,16 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
   const size_t desc_bytes = sizeof(PassDesc) * 2 * (kMaxBuckets + 1);
   // work buffer: bucket counts, bucket lists, forward values
   const size_t f_words = use_u ? (((size_t)ngroups << kmax) * M * 32u) : (((size_t)nvirt << kmax) * PS);
-  const size_t need = ((kMaxBuckets + 1) + (size_t)(kMaxBuckets + 1) * cnt + f_words) * 4 + 256;
+  const size_t head_words = (size_t)(kMaxBuckets + 1) + 2u * ((size_t)tcap + 1u);   // bucket counts, per-degree counts and cursors
+  const size_t need = (head_words + (size_t)(kMaxBuckets + 1) * cnt + f_words) * 4 + 256;
   int rc = w.fwd_buf.reserve(need);
   if (rc) return rc;
   const bool fresh_descs = w.descs.p == nullptr;
   if ((rc = w.descs.reserve(desc_bytes))) return rc;
   PassDesc *d_descs = (PassDesc *)w.descs.p;
   uint32_t *counts = (uint32_t *)w.fwd_buf.p;
-  uint32_t *lists = counts + (kMaxBuckets + 1);
+  uint32_t *by_deg = counts + (kMaxBuckets + 1);
+  uint32_t *lists = counts + head_words;
   // forward values are read and written as 16-byte vectors
   uint32_t *F = (uint32_t *)(((uintptr_t)(lists + (size_t)(kMaxBuckets + 1) * cnt) + 15) & ~(uintptr_t)15);
   std::vector<PassDesc> fwd(kMaxBuckets + 1), bwd(kMaxBuckets + 1);
@@ -368,9 +370,22 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
     w.descs_t = t;
     w.descs_kmax = kmax;
   }
-  BCHFFT_CUDA_TRY(cudaMemsetAsync(counts, 0, (kMaxBuckets + 1) * 4, st));
-  BCHFFT_RUN(k_bucket, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, (const int32_t *)s.flag,
-             (const uint32_t *)s.L, tcap, (uint32_t)cnt, counts, lists);
+  BCHFFT_CUDA_TRY(cudaMemsetAsync(counts, 0, head_words * 4, st));
+  // locators of degree 1 and 2 are solved in closed form by k_bucket_count itself (BCHFFT_LOCATE_DIRECT=0:
+  // all degrees go through the search)
+  const char *denv = getenv("BCHFFT_LOCATE_DIRECT");
+  const uint32_t direct_max = denv ? (uint32_t)(atoi(denv) < 0 ? 0 : (atoi(denv) > 2 ? 2 : atoi(denv))) : 2u;
+  {
+    const size_t smem_b = sizeof(uint32_t) * 2u * ((size_t)tcap + 1u);
+    BCHFFT_ENSURE_SMEM(k_bucket_count, c->f->device, smem_b);
+    BCHFFT_ENSURE_SMEM(k_bucket_scatter, c->f->device, smem_b);
+    BCHFFT_RUN(k_bucket_count, dim3((unsigned)((cnt + 255) / 256)), dim3(256), smem_b, st, (const int32_t *)s.flag,
+               (const uint32_t *)s.L, tcap, (uint32_t)cnt, by_deg, direct_max, (const uint32_t *)s.elp, c->d,
+               c->f->order, (const uint32_t *)c->f->d_log, (const uint32_t *)c->f->d_exp,
+               (const uint32_t *)c->f->d_qsolve, s.count, s.positions, s.pos_stride);
+    BCHFFT_RUN(k_bucket_scatter, dim3((unsigned)((cnt + 255) / 256)), dim3(256), smem_b, st, (const int32_t *)s.flag,
+               (const uint32_t *)s.L, tcap, (uint32_t)cnt, counts, by_deg, lists, direct_max);
+  }
   if (use_u) {
     // forward phase of all buckets in one launch (blockIdx.y = K - 1): 256 coefficient columns per CTA,
     // i.e. 2^(8-K) slabs; CTAs beyond a bucket's population exit
@@ -394,8 +409,9 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
     const size_t smem_u = sizeof(uint32_t) * (32u * M * 32u + qcap);
     BCHFFT_ENSURE_SMEM(k_locate_u<M>, c->f->device, smem_u);
     BCHFFT_RUN(k_locate_u<M>, dim3(gx, ngroups), dim3(kNtLoc), smem_u, st, (const uint32_t *)F,
-               (const uint32_t *)counts, (const uint32_t *)lists, (uint32_t)cnt, (uint32_t)kmax, c->f->tab,
-               (const uint32_t *)c->f->d_errloc, s.count, s.positions, s.pos_stride, qcap);
+               (const uint32_t *)counts, (const uint32_t *)lists,
+               getenv("BCHFFT_LOCU_NOSKIP") ? (const uint32_t *)nullptr : (const uint32_t *)s.L, (uint32_t)cnt,
+               (uint32_t)kmax, c->f->tab, (const uint32_t *)c->f->d_errloc, s.count, s.positions, s.pos_stride, qcap);
     return BCHFFT_OK;
   }
   for (int K = 1; K <= kmax; K++) {

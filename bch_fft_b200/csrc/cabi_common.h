@@ -82,6 +82,7 @@ struct bchfft_field {
   std::vector<uint32_t> h_exp, h_log;
   uint32_t *d_tw = nullptr, *d_gam = nullptr, *d_perm_exp = nullptr, *d_perm_nat = nullptr;
   uint32_t *d_exp = nullptr, *d_log = nullptr, *d_errloc = nullptr;
+  uint32_t *d_qsolve = nullptr;   // {trace mask, h_0 .. h_(m-1)}: y^2 + y = u solver of the degree-2 root finder
   uint32_t twist_free = 0;               // depths whose twist is the identity (gm_plan.h)
   bchfft::FftTables tab;
   std::map<int, bchfft::GmPlan> plans;   // keyed by K

@@ -307,10 +307,38 @@ extern "C" int bchfft_field_create(int device, uint32_t m, const uint32_t *exp, 
     errloc[p] = k ? (n - 1u) - log[k] : 0xFFFFFFFFu;
   }
   f->twist_free = c.twist_free;
+  // y^2 + y = u, solved bit by bit (k_bucket's closed-form roots of degree-2 locators): trace of every
+  // x^k, one trace-one element tau, h_k with h_k^2 + h_k = x^k + Tr(x^k) tau
+  std::vector<uint32_t> qsolve(1u + m, 0u);
+  {
+    auto mul = [&](uint32_t a, uint32_t b) -> uint32_t {
+      if (!a || !b) return 0u;
+      uint32_t sum = log[a] + log[b];
+      if (sum >= n - 1u) sum -= n - 1u;
+      return exp[sum];
+    };
+    uint32_t tau = 0u;
+    for (uint32_t k = 0; k < m; k++) {
+      uint32_t v = 1u << k, tr = 0u;
+      for (uint32_t r = 0; r < m; r++) {
+        tr ^= v;
+        v = mul(v, v);
+      }
+      if (tr & 1u) {
+        qsolve[0] |= 1u << k;
+        if (!tau) tau = 1u << k;
+      }
+    }
+    for (uint32_t k = 0; k < m; k++) {
+      uint32_t y = 0u;
+      solve_artin_schreier((int)m, mul, (1u << k) ^ (((qsolve[0] >> k) & 1u) ? tau : 0u), &y);
+      qsolve[1u + k] = y;
+    }
+  }
   int rc = BCHFFT_OK;
   if ((rc = upload_vec(c.tw, &f->d_tw)) || (rc = upload_vec(c.gam, &f->d_gam)) ||
       (rc = upload_vec(perm_exp, &f->d_perm_exp)) || (rc = upload_vec(perm_nat, &f->d_perm_nat)) ||
-      (rc = upload_vec(errloc, &f->d_errloc)) ||
+      (rc = upload_vec(errloc, &f->d_errloc)) || (rc = upload_vec(qsolve, &f->d_qsolve)) ||
       (rc = upload_vec(f->h_exp, &f->d_exp)) || (rc = upload_vec(f->h_log, &f->d_log))) {
     bchfft_field_destroy(f);
     return rc;
@@ -353,6 +381,7 @@ extern "C" void bchfft_field_destroy(bchfft_field *f)
   cudaFree(f->d_perm_exp);
   cudaFree(f->d_perm_nat);
   cudaFree(f->d_errloc);
+  cudaFree(f->d_qsolve);
   cudaFree(f->d_exp);
   cudaFree(f->d_log);
   f->ws.release();

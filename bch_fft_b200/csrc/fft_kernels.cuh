@@ -692,8 +692,12 @@ __device__ __forceinline__ void tile_butterfly_r4(uint32_t *S, uint32_t T, uint3
     const uint32_t G = gam_d[p0 >> (d + 1)];
     if (UNI && uni) {
       if (G) {
+#if BCHFFT_R4_MAD2
+        bs_mad_uniform2<M>(e0, e2, e1, e3, G);
+#else
         bs_mad_uniform<M>(e0, e2, G);
         bs_mad_uniform<M>(e1, e3, G);
+#endif
       }
     } else if (G) {
       bs_mad_scalar<M>(e0, e2, G);

@@ -39,3 +39,22 @@ def decode_input(rec, encode):
 
 def flip(word, pos):
     word[pos >> 6] ^= np.uint64(1) << np.uint64(pos & 63)
+
+
+def low_degree_locators(m, t, rng):
+    """locators of degree <= 3 incl. the degenerate shapes of the closed-form path: c2 = 0 under L = 2,
+    c1 = 0 (double root), c1 = c2 = 0, roots outside the field (Tr(c2 / c1^2) = 1)"""
+    n, d = 1 << m, 2 * t + 1
+    rows = []
+    for L in (1, 2, 3):
+        for _ in range(24):
+            e = np.zeros(d + 1, np.uint32)
+            e[0] = 1
+            e[1: L + 1] = rng.integers(1, n, L)
+            rows.append((L, e))
+    for c1, c2 in ((0, 0), (0, 5), (7, 0), (0, 1), (1, 1), (1, 0), (n - 1, n - 1), (3, n - 2)):
+        e = np.zeros(d + 1, np.uint32)
+        e[0], e[1], e[2] = 1, c1, c2
+        rows.append((2, e))
+        rows.append((1, e))
+    return rows

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from bch_fft_b200 import _lib, api, synth
-from tests.common import GOLDEN, additive_input, decode_input, flip, fnv64
+from tests.common import GOLDEN, additive_input, decode_input, flip, fnv64, low_degree_locators
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -124,7 +124,7 @@ def _words_for(pc, n, t, B, rng):
     words = np.zeros((B, pc.words), np.uint64)
     for b in range(B):
         w = pool[b % 4].copy()
-        ne = [0, 1, t, t // 2, t + 1, t + 2, t + 3][b % 7] if b < 56 else int(rng.integers(0, t + 1))
+        ne = [0, 1, 2, t, t // 2, t + 1, t + 2, t + 3][b % 8] if b < 56 else int(rng.integers(0, t + 1))
         pos = rng.choice(n, min(ne, n), replace=False)
         if b % 5 == 0 and ne:
             pos[0] = 0                       # bit-0 quirk (bch.c:479-488)
@@ -172,6 +172,37 @@ def test_emu_bch_stages_and_decode_vs_oracle(emu_libs, port, n, t):
     rok, rcorr, rw = pc.decode_batch(words)
     assert (ok == rok).all() and (corr == rcorr).all() and (out == rw).all()
     assert (ok == 0).any() and (ok == 1).any()
+    cabi.bchfft_code_destroy(c)
+    cabi.bchfft_field_destroy(h)
+
+
+@pytest.mark.parametrize("n,t", [(63, 5), (255, 8), (1023, 10), (8191, 16)])
+def test_emu_closed_form_roots_of_low_degree_locators(emu_libs, port, n, t):
+    """k_bucket solves locators of degree 1 and 2 in closed form (bch.c:406-490 searches every point):
+    same root lists as the oracle's search, and as the device search with the shortcut switched off"""
+    cabi, _ = emu_libs
+    pc = port.code(n, t)
+    h = _field(cabi, port, pc.m)
+    c = C.c_void_p()
+    _lib.check(cabi, cabi.bchfft_code_create(h, 2 * t + 1, n, pc.gen.ctypes.data, pc.gen_degree,
+                                             C.byref(c)), "code")
+    d = 2 * t + 1
+    rows = low_degree_locators(pc.m, t, np.random.default_rng(n))
+    B = len(rows)
+    elp = np.stack([e for _, e in rows])
+    L = np.array([l for l, _ in rows], np.uint32)
+    for direct in (("2", "0") if n < 2000 else ("2",)):     # the emulated search of GF(2^13) takes minutes
+        os.environ["BCHFFT_LOCATE_DIRECT"] = direct
+        try:
+            posn = np.zeros((B, d + 1), np.uint32)
+            cnt = np.zeros(B, np.uint32)
+            _lib.check(cabi, cabi.bchfft_bch_locate_host(c, elp.ctypes.data, L.ctypes.data, B,
+                                                         posn.ctypes.data, cnt.ctypes.data), "locate")
+        finally:
+            del os.environ["BCHFFT_LOCATE_DIRECT"]
+        for b in range(B):
+            pr = pc.locate(elp[b, : L[b] + 1], int(L[b]))
+            assert cnt[b] == len(pr) and (posn[b, : cnt[b]] == pr).all(), (direct, b, L[b], elp[b, :3])
     cabi.bchfft_code_destroy(c)
     cabi.bchfft_field_destroy(h)
 

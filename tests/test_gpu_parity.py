@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from bch_fft_b200 import _lib, api, synth
-from tests.common import GOLDEN, additive_input, decode_input, flip, fnv64
+from tests.common import GOLDEN, additive_input, decode_input, flip, fnv64, low_degree_locators
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -259,6 +259,38 @@ def test_encode_corrupt_decode_round_trip_on_device_encoder(gpu_libs):
         words[rows, pos // 64] ^= np.uint64(1) << (pos % 64).astype(np.uint64)
     ok, corr, out = code.decode_batch(words)
     assert (ok == 1).all() and (corr == nerr).all() and (out == clean).all()
+
+
+@pytest.mark.parametrize("n,t", [(63, 5), (1023, 10), (8191, 16), (65535, 100)])
+def test_closed_form_roots_of_low_degree_locators(gpu_libs, port, n, t):
+    """k_bucket solves locators of degree 1 and 2 in closed form (bch.c:406-490 searches every point):
+    same root lists as the oracle's search and as the device search with the shortcut switched off,
+    including c1 = 0 (double root), c2 = 0 under L = 2 and roots outside the field"""
+    cabi, _ = gpu_libs
+    pc = port.code(n, t)
+    h = _field(cabi, port, pc.m)
+    c = C.c_void_p()
+    _lib.check(cabi, cabi.bchfft_code_create(h, 2 * t + 1, n, pc.gen.ctypes.data, pc.gen_degree,
+                                             C.byref(c)), "code")
+    d = 2 * t + 1
+    rows = low_degree_locators(pc.m, t, np.random.default_rng(n))
+    B = len(rows)
+    elp = np.stack([e for _, e in rows])
+    L = np.array([l for l, _ in rows], np.uint32)
+    for direct in ("2", "0"):
+        os.environ["BCHFFT_LOCATE_DIRECT"] = direct
+        try:
+            posn = np.zeros((B, d + 1), np.uint32)
+            cnt = np.zeros(B, np.uint32)
+            _lib.check(cabi, cabi.bchfft_bch_locate_host(c, elp.ctypes.data, L.ctypes.data, B,
+                                                         posn.ctypes.data, cnt.ctypes.data), "locate")
+        finally:
+            del os.environ["BCHFFT_LOCATE_DIRECT"]
+        for b in range(B):
+            pr = pc.locate(elp[b, : L[b] + 1], int(L[b]))
+            assert cnt[b] == len(pr) and (posn[b, : cnt[b]] == pr).all(), (direct, b, L[b], elp[b, :3])
+    cabi.bchfft_code_destroy(c)
+    cabi.bchfft_field_destroy(h)
 
 
 def test_root_queue_drain_and_overflow_paths_on_device(gpu_libs):
