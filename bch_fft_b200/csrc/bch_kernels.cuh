@@ -410,7 +410,7 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
                      uint32_t batch, const uint32_t *__restrict__ gexp, const uint32_t *__restrict__ glog,
                      uint32_t *__restrict__ bm, uint32_t *__restrict__ elp, uint32_t *__restrict__ Lout,
                      const uint32_t *__restrict__ acc, const uint32_t *__restrict__ parity, uint32_t nodd,
-                     uint32_t elp_limit, uint32_t cs_sm)
+                     uint32_t elp_limit, uint32_t cs_sm, uint32_t binary_word)
 {
   static_assert(LPC == 1 || (SM && LPC <= 32 && (LPC & (LPC - 1)) == 0), "lane groups need the shared-memory variant");
   typedef typename std::conditional<SM, uint16_t, uint32_t>::type coef_t;
@@ -536,6 +536,14 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
     }
     pair_sync();
     for (uint32_t i = 0; i + 1 < d; ++i) {
+      // Syndromes of a binary word are power sums in characteristic 2 (S_2j = S_j^2), for which every
+      // second discrepancy -- the one that brings in S_(i+1) with i + 1 even -- is zero whatever the
+      // word (Berlekamp's binary simplification).  The decode pipeline says so (binary_word); the
+      // stage-level entry point takes arbitrary syndrome arrays and computes every discrepancy.
+      if (binary_word && (i & 1u)) {
+        gap++;
+        continue;
+      }
       // four terms in flight: the loads of a batch are issued before the first table lookup, so the
       // dependent shared-memory latencies (coefficient -> log -> exp) overlap instead of adding up
       uint32_t disc = sub == 0u ? (uint32_t)s[(i + 1) * ss] : 0u;
@@ -627,7 +635,8 @@ __global__ void k_bm(const uint32_t *__restrict__ syn, int32_t *__restrict__ fla
 template <int M>
 __global__ void k_bm_wide(const uint32_t *__restrict__ syn, const int32_t *__restrict__ flag, uint32_t d,
                           uint32_t batch, const uint32_t *__restrict__ gexp, const uint32_t *__restrict__ glog,
-                          uint32_t *__restrict__ elp, uint32_t *__restrict__ Lout, uint32_t elp_limit)
+                          uint32_t *__restrict__ elp, uint32_t *__restrict__ Lout, uint32_t elp_limit,
+                          uint32_t binary_word)
 {
   const uint32_t order = (1u << M) - 1u;
   BCHFFT_DYN_SMEM(uint32_t, poly);
@@ -667,7 +676,13 @@ __global__ void k_bm_wide(const uint32_t *__restrict__ syn, const int32_t *__res
   uint32_t L = 0;
   if (flag[cw]) {
     uint32_t degA = 0, degB = 0, degC = 0, gap = 1, inv_b_log = 0, slot = 0;
-    for (uint32_t i = 0; i + 1 < d; ++i, slot = slot == 2u ? 0u : slot + 1u) {
+    // (the reduction cells rotate per EXECUTED iteration: a skipped one has no barrier)
+    auto next_slot = [&]() { slot = slot == 2u ? 0u : slot + 1u; };
+    for (uint32_t i = 0; i + 1 < d; ++i) {
+      if (binary_word && (i & 1u)) {   // see k_bm: this discrepancy is zero for the syndromes of a binary word
+        gap++;
+        continue;
+      }
       uint32_t part = 0u;
       for (uint32_t j = 1u + tid; j <= degC; j += nt) part ^= gf_mul<M>(C[j], sc[i + 1u - j]);
       add_disc(slot, part);
@@ -680,6 +695,7 @@ __global__ void k_bm_wide(const uint32_t *__restrict__ syn, const int32_t *__res
       }
       if (!disc) {
         gap++;
+        next_slot();
         continue;
       }
       const uint32_t dlog = glog[disc];
@@ -716,6 +732,7 @@ __global__ void k_bm_wide(const uint32_t *__restrict__ syn, const int32_t *__res
       }
       { uint32_t *t = C; C = A; A = t; }
       degC = degA;
+      next_slot();
     }
   }
   __syncthreads();

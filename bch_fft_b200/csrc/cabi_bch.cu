@@ -266,7 +266,7 @@ static bool bm_in_smem(const bchfft_code *c, BmShape *out)
 
 template <int M, int LPC>
 static int launch_bm_sm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t st, bool fused, uint32_t elp_limit,
-                        const BmShape &b)
+                        const BmShape &b, bool binary_word)
 {
   const unsigned per_cta = b.nt / LPC;
   BCHFFT_ENSURE_SMEM((k_bm<M, true, LPC>), c->f->device, b.smem);
@@ -274,16 +274,19 @@ static int launch_bm_sm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream
              (const uint32_t *)s.syn, s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
              (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L,
              fused ? (const uint32_t *)s.acc : (const uint32_t *)nullptr, (const uint32_t *)s.parity, c->nodd,
-             elp_limit, (uint32_t)b.cs);
+             elp_limit, (uint32_t)b.cs, binary_word ? 1u : 0u);
   return BCHFFT_OK;
 }
 
 // fused: the syndromes are still bitsliced accumulators (launch_syndrome(..., finish = false));
 // only valid when bm_in_smem()
 template <int M>
+// binary_word: the syndromes were computed from binary words by this library (decode pipeline), which lets the
+// kernels skip the discrepancies that are zero for power sums in characteristic 2
 static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t st, bool fused = false,
-                     uint32_t elp_limit = 0xFFFFFFFFu)
+                     uint32_t elp_limit = 0xFFFFFFFFu, bool binary_word = false)
 {
+  if (getenv("BCHFFT_BM_ALL_DISC")) binary_word = false;
   if (!fused && bm_wide(c, cnt)) {
     const size_t smem_w = sizeof(uint32_t) * ((size_t)4 * c->d + 3u);
     unsigned ntw = ((c->t + 1u + 31u) / 32u) * 32u;
@@ -291,19 +294,19 @@ static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t 
     BCHFFT_ENSURE_SMEM(k_bm_wide<M>, c->f->device, smem_w);
     BCHFFT_RUN(k_bm_wide<M>, dim3((unsigned)cnt), dim3(ntw), smem_w, st, (const uint32_t *)s.syn,
                (const int32_t *)s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
-               (const uint32_t *)c->f->d_log, s.elp, s.L, elp_limit);
+               (const uint32_t *)c->f->d_log, s.elp, s.L, elp_limit, binary_word ? 1u : 0u);
     return BCHFFT_OK;
   }
   BmShape b;
   if constexpr (M <= 14) {
     if (bm_in_smem<M>(c, &b)) {
       switch (b.lpc) {
-        case 1: return launch_bm_sm<M, 1>(c, cnt, s, st, fused, elp_limit, b);
-        case 2: return launch_bm_sm<M, 2>(c, cnt, s, st, fused, elp_limit, b);
-        case 4: return launch_bm_sm<M, 4>(c, cnt, s, st, fused, elp_limit, b);
-        case 8: return launch_bm_sm<M, 8>(c, cnt, s, st, fused, elp_limit, b);
-        case 16: return launch_bm_sm<M, 16>(c, cnt, s, st, fused, elp_limit, b);
-        default: return launch_bm_sm<M, 32>(c, cnt, s, st, fused, elp_limit, b);
+        case 1: return launch_bm_sm<M, 1>(c, cnt, s, st, fused, elp_limit, b, binary_word);
+        case 2: return launch_bm_sm<M, 2>(c, cnt, s, st, fused, elp_limit, b, binary_word);
+        case 4: return launch_bm_sm<M, 4>(c, cnt, s, st, fused, elp_limit, b, binary_word);
+        case 8: return launch_bm_sm<M, 8>(c, cnt, s, st, fused, elp_limit, b, binary_word);
+        case 16: return launch_bm_sm<M, 16>(c, cnt, s, st, fused, elp_limit, b, binary_word);
+        default: return launch_bm_sm<M, 32>(c, cnt, s, st, fused, elp_limit, b, binary_word);
       }
     }
   }
@@ -314,7 +317,7 @@ static int launch_bm(bchfft_code *c, size_t cnt, const Scratch &s, cudaStream_t 
   BCHFFT_RUN((k_bm<M, false, 1>), dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st,
              (const uint32_t *)s.syn, s.flag, c->d, (uint32_t)cnt, (const uint32_t *)c->f->d_exp,
              (const uint32_t *)c->f->d_log, s.bm, s.elp, s.L, (const uint32_t *)nullptr,
-             (const uint32_t *)nullptr, 0u, elp_limit, 0u);
+             (const uint32_t *)nullptr, 0u, elp_limit, 0u, binary_word ? 1u : 0u);
   return BCHFFT_OK;
 }
 
@@ -466,7 +469,7 @@ static int decode_run(bchfft_code *c, bchfft_code::WorkSet &w, uint64_t *d_words
     const bool fused = bm_sm && !bm_wide(c, cnt) && !(fenv && atoi(fenv) == 0);
     BCHFFT_CUDA_TRY(cudaMemsetAsync(w.scratch.p, 0, zero_bytes(c, cnt, M, !bm_sm), st));
     if ((rc = launch_syndrome<M>(c, w, wp, cnt, s, st, !fused))) return rc;
-    if ((rc = launch_bm<M>(c, cnt, s, st, fused, c->t))) return rc;
+    if ((rc = launch_bm<M>(c, cnt, s, st, fused, c->t, true))) return rc;
     if ((rc = launch_locate<M>(c, w, cnt, s, c->t, st))) return rc;
     BCHFFT_RUN(k_correct, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, wp, c->wpc,
                   (uint32_t)cnt, (const int32_t *)s.flag, (const uint32_t *)s.L, c->t,
@@ -955,7 +958,11 @@ static size_t flip_threads()
 {
   const char *env = getenv("BCHFFT_FLIP_THREADS");
   if (env && atoi(env) >= 1 && atoi(env) <= 64) return (size_t)atoi(env);
-  size_t n = std::thread::hardware_concurrency() / 4;
+  // a quarter of the host's hardware threads, shared with the other ranks of a one-process-per-GPU job
+  // (torchrun exports LOCAL_WORLD_SIZE)
+  const char *lws = getenv("LOCAL_WORLD_SIZE");
+  const size_t ranks = lws && atoi(lws) >= 1 ? (size_t)atoi(lws) : 1;
+  size_t n = std::thread::hardware_concurrency() / (4 * ranks);
   return n < 2 ? 2 : (n > 8 ? 8 : n);
 }
 

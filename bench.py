@@ -397,8 +397,12 @@ def decode_section(cx, length, t, B, steps, warmup, seed, headline=False, e2e_st
             if i:
                 tsum += cx.max_over_ranks(dt)
         assert (h_ok.numpy() == ok_gpu).all()
+        # what bch_decode_batch brings back (cabi_bch.cu, BCHFFT_D2H_MODE): verdicts + error positions from
+        # 8192 codewords on (host threads flip the bits in the caller's array), whole words below that
+        mode = os.environ.get("BCHFFT_D2H_MODE") or ("positions" if B >= 8192 else "words")
+        d2h = B * (1 + 4 + 4 * (t + 1)) if mode == "positions" else B * (W * 8 + 1 + 4)
         e2e = {"value": cx.world * B * e2e_steps / tsum, "unit": "codewords/s",
-               "h2d_bytes_per_step": B * W * 8, "d2h_bytes_per_step": B * (W * 8 + 1 + 4),
+               "h2d_bytes_per_step": B * W * 8, "d2h_bytes_per_step": d2h, "result_mode": mode,
                "steps": e2e_steps, "api": "bch_decode_batch (host C library, include/bch.h)",
                "timer": "host wall clock around the synchronous call, max over ranks"}
         out_head = h_work.numpy().view(np.uint64)

@@ -316,6 +316,33 @@ def test_root_queue_drain_and_overflow_paths_on_device(gpu_libs):
         assert res.returncode == 0 and "ok" in res.stdout, (q, res.stderr[-2000:])
 
 
+@pytest.mark.parametrize("env", ["BCHFFT_BM_LPC=4", "BCHFFT_BM_LPC=16", "BCHFFT_BM_ALL_DISC=1", "BCHFFT_LOCU_NOSKIP=1",
+                                 "BCHFFT_LOCATE_DIRECT=0", "BCHFFT_LOCATE_U=0"])
+def test_alternative_kernel_routes_give_the_same_bits(gpu_libs, env):
+    """every route switch of INTEGRATION.md section 6 that round 2 added: other lane-group sizes of the
+    Berlekamp-Massey kernel, all discrepancies computed, zero forward values evaluated anyway, no
+    closed-form roots, tile-engine root search -- same verdicts and words as the oracle at t = 16 and 64"""
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from bch_fft_b200 import api, synth\n"
+        "from oracle.pyoracle import Port\n"
+        "host = api.Host(); P = Port()\n"
+        "for n, t, B in ((8191, 16, 5000), (8191, 64, 1500)):\n"
+        "    code = host.bch_gen_code(n, 2 * t + 1); pc = P.code(n, t)\n"
+        "    bits = (synth.splitmix64(11, 8 * code.data_bits) & np.uint64(1)).astype(np.uint32).reshape(8, -1)\n"
+        "    pool = np.stack([code.encode(b) for b in bits])\n"
+        "    words, _ = synth.corrupt_codewords(pool, n, t, B, 11, beyond_fraction=0.05)\n"
+        "    ok, corr, out = code.decode_batch(words)\n"
+        "    rok, rcorr, rout = pc.decode_batch(words)\n"
+        "    assert (ok == rok).all() and (corr == rcorr).all() and (out == rout).all(), (n, t)\n"
+        "print('ok')\n")
+    k, v = env.split("=")
+    res = subprocess.run([os.sys.executable, "-c", code], env=dict(os.environ, **{k: v}), capture_output=True,
+                         text=True)
+    assert res.returncode == 0 and "ok" in res.stdout, (env, res.stderr[-2000:])
+
+
 def test_reference_demo_sources_build_and_pass(gpu_libs):
     """the reference's bchdemo source, UNCHANGED, linked against our libraries (drop-in check);
     needs the reference tree, so it only runs where /root/reference exists"""
