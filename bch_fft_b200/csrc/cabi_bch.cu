@@ -343,7 +343,10 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
   const unsigned nvirt = ns + (unsigned)kmax;           // sum_K ceil(count_K / 32) <= ns + kmax
   // low locator degrees: lanes = slabs, warp-uniform multipliers (k_locate_u)
   const char *uenv = getenv("BCHFFT_LOCATE_U");
-  const bool use_u = kmax <= kLocUMaxK && M >= 5 && M <= 22 && !(uenv && atoi(uenv) == 0);
+  // (buckets K = 6, 7 recompute part of their first step per tile: worth it for whole slab groups only --
+  // a single bch_decode at n = 65535, t = 100 takes 0.44 ms through k_locate and 0.63 ms through k_locate_u)
+  const bool use_u = (kmax <= 5 || (kmax <= kLocUMaxK && cnt >= 4096)) && M >= 5 && M <= 22 &&
+                     !(uenv && atoi(uenv) == 0);
   const unsigned ngroups = (unsigned)(cnt / 1024) + (unsigned)kmax + 1u;   // >= sum_K ceil(ceil(count_K/32)/32)
   // descriptors: [0, kMaxBuckets] backward (butterfly) passes, [kMaxBuckets + 1, 2 kMaxBuckets + 1] forward passes
   const size_t desc_bytes = sizeof(PassDesc) * 2 * (kMaxBuckets + 1);

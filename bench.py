@@ -68,13 +68,15 @@ def peaks():
         return 6650.0, 1965.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_counters(kernel):
+def ncu_counters(kernel, tag=None):
     """per-unit counters of `kernel` from the committed ncu capture (profiles/traffic.json, made by
     tools/make_traffic.py from an `ncu --set full` export): DRAM bytes and alu-pipe warp instructions per
-    codeword / field point; None when the kernel has no capture"""
+    codeword / field point; None when the kernel has no capture.  A side configuration (`tag`, e.g. "t64")
+    only uses counters captured on that configuration ("kernel@tag"): per-unit work depends on the code."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(kernel)
+            d = json.load(f)
+        return d.get(f"{kernel}@{tag}") if tag else d.get(kernel)
     except Exception:
         return None
 
@@ -304,7 +306,7 @@ class Ctx:
             self.barrier()
         return self.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
 
-    def roofline(self, prof, units, bytes_per_unit, step_ms, unit_name):
+    def roofline(self, prof, units, bytes_per_unit, step_ms, unit_name, tag=None):
         """roofline of the dominant kernel: algorithmic bytes of one step / the kernel's device time per
         step (all of its launches), against the measured HBM peak; plus the integer-pipe view: alu-pipe
         warp instructions per unit (ncu capture) x units/s against 148 SMs x 64 lanes x SM clock"""
@@ -312,7 +314,7 @@ class Ctx:
         top = max(prof, key=lambda k: prof[k][0])
         top_ms, top_n = prof[top]
         achieved = units * bytes_per_unit / (top_ms * 1e-3) / 1e9
-        cnt = ncu_counters(top)
+        cnt = ncu_counters(top, tag)
         r = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": self.peak_gbs, "unit": "GB/s",
              "frac": achieved / self.peak_gbs,
              "traffic": (cnt["dram_bytes_per_unit"] * units / top_n) if cnt else None,
@@ -374,7 +376,9 @@ def decode_section(cx, length, t, B, steps, warmup, seed, headline=False, e2e_st
         prof = cx._lib.profile(cx.lib, run)
         ok_gpu = d_ok.cpu().numpy()
         corr_gpu = d_corr.cpu().numpy().view(np.uint32)
-    roofline = cx.roofline(prof, B, bytes_per_cw, step_ms, "codeword")
+    # ncu counters per codeword depend on the code: the headline uses the headline capture, t = 64 / 200 their own
+    roofline = cx.roofline(prof, B, bytes_per_cw, step_ms, "codeword",
+                           tag=None if (headline or (length, t) == (8191, 16)) else f"t{t}")
     roofline["note"] = ("integer/LOP3-bound bitsliced GF(2^m) arithmetic: the HBM fraction is low by construction; "
                         "int_pipe and profiles/*_ncu_summary_decode.txt give the pipe utilisation")
     out_head = None
