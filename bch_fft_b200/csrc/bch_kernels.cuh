@@ -1381,74 +1381,110 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
 
 // ---- systematic encoder (bch.c:492-506) -------------------------------------
 // codeword = data * X^dg + (data * X^dg mod g): data bit i -> codeword bit i + dg, parity in bits
-// 0 .. dg-1.  One thread per codeword, byte-wise division by g: R <- (R << 8) ^ T[top byte of R ^
-// data byte], T[v] = v(X) X^dg mod g (256 rows of NW 64-bit words, staged in shared memory by the
-// CTA; dynamic smem = 256 * NW * 8 bytes).  Requires 8 <= dg <= 64 NW.  data: [batch][dwords]
-// packed data bits (bit i of item = bit i % 64 of word i / 64), only the first data_bits count.
+// 0 .. dg-1.  One thread per codeword divides by g byte-wise: R <- (R << 8) ^ T[top byte of R ^
+// data byte], T[v] = v(X) X^dg mod g (256 rows of NW 64-bit words in shared memory).  Requires
+// 8 <= dg <= 64 NW.  data: [batch][dwords] packed data bits (bit i of item = bit i % 64 of word
+// i / 64), only the first data_bits count.
+// Memory side: a warp owns 32 codewords.  Their data travel through a [32][33]-word shared tile in
+// chunks of 32 words per codeword, loaded with the lanes along a codeword (128-byte rows) and read
+// back with one codeword per lane (conflict-free), so that neither the loads of the division nor the
+// stores of the shifted copy data << dg (done by the warp together, lanes along the codeword) touch a
+// sector for 8 bytes at a time -- round 1's one-thread-per-row version ran at 3 % of the copy bandwidth.
+// The owner of a codeword finally writes the words that hold its parity bits.
+// grid = ceil(batch / 128), 128 threads; dynamic smem = 256 * NW * 8 + 4 * 32 * 33 * 4 bytes.
 template <int NW>
 __global__ void __launch_bounds__(128)
 k_encode(const uint64_t *__restrict__ data, uint32_t dwords, uint32_t data_bits, uint32_t dg,
          const uint64_t *__restrict__ table, uint64_t *__restrict__ cw_out, uint32_t wpc, uint32_t batch)
 {
   BCHFFT_DYN_SMEM(uint64_t, T);
+  uint32_t *tiles = reinterpret_cast<uint32_t *>(T + 256u * NW);
   for (uint32_t i = threadIdx.x; i < 256u * NW; i += blockDim.x) T[i] = table[i];
   __syncthreads();
-  const uint32_t cw = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cw >= batch) return;
-  const uint64_t *dsrc = data + (size_t)cw * dwords;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t *S = tiles + warp * (32u * 33u);
+  const uint32_t cw0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 32u;     // first codeword of the warp
+  const uint32_t cw = cw0 + lane;                                           // this lane's codeword
+  const uint32_t *d32 = reinterpret_cast<const uint32_t *>(data);
+  const size_t dstride = (size_t)dwords * 2u;                               // 32-bit words per data row
+  const uint32_t nw32 = (data_bits + 31u) >> 5;                             // data words in use
+  const uint32_t tail = data_bits & 31u;                                    // bits of the last one (0 = all)
+  // data word w of codeword c, bits beyond data_bits cleared, zero outside the row
+  auto dword = [&](uint32_t c, uint32_t w) -> uint32_t {
+    if (w >= nw32 || c >= batch) return 0u;
+    uint32_t x = d32[(size_t)c * dstride + w];
+    if (w == nw32 - 1u && tail) x &= (1u << tail) - 1u;
+    return x;
+  };
+
+  // division: chunks of 32 data words from the top of the polynomial down
   uint64_t R[NW];
 #pragma unroll
   for (int k = 0; k < NW; ++k) R[k] = 0ull;
   const uint32_t tw = (dg - 8u) >> 6, tsh = (dg - 8u) & 63u;   // top byte of R = bits dg-8 .. dg-1
   const uint32_t hw = (dg - 1u) >> 6;                           // last word of R in use
   const uint64_t hmask = (dg & 63u) ? ((1ull << (dg & 63u)) - 1ull) : ~0ull;
-  const uint32_t nbytes = (data_bits + 7u) >> 3;
-  for (uint32_t b = nbytes; b-- > 0;) {
-    uint64_t dw = dsrc[b >> 3];
-    const uint32_t last = data_bits - 1u;
-    if ((b >> 3) == (last >> 6) && (last & 63u) != 63u) dw &= (2ull << (last & 63u)) - 1ull;   // bits >= data_bits
-    const uint32_t dbyte = (uint32_t)(dw >> ((b & 7u) * 8u)) & 255u;
-    uint32_t top = 0u;
+  const uint32_t nchunks = (nw32 + 31u) >> 5;
+  for (uint32_t ch = nchunks; ch-- > 0;) {
+    const uint32_t base = ch * 32u;
+    for (uint32_t c = 0; c < 32u; ++c) S[c * 33u + lane] = dword(cw0 + c, base + lane);
+    __syncwarp();
+    for (uint32_t k = 32u; k-- > 0;) {
+      if (base + k >= nw32) continue;                           // (uniform: nw32 is a kernel argument)
+      const uint32_t w = S[lane * 33u + k];
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      if ((uint32_t)k == tw) top |= (uint32_t)(R[k] >> tsh);
-      if ((uint32_t)k == tw + 1u && tsh > 56u) top |= (uint32_t)(R[k] << (64u - tsh));
-    }
-    const uint64_t *row = T + (size_t)((top ^ dbyte) & 255u) * NW;
+      for (int by = 3; by >= 0; --by) {
+        if ((base + k) * 32u + (uint32_t)by * 8u >= data_bits) continue;   // whole byte beyond the data
+        const uint32_t dbyte = (w >> (by * 8)) & 255u;
+        uint32_t top = 0u;
 #pragma unroll
-    for (int k = NW - 1; k >= 0; --k) {
-      const uint64_t lo = k > 0 ? (R[k - 1] >> 56) : 0ull;
-      R[k] = ((R[k] << 8) | lo) ^ row[k];
-    }
+        for (int q = 0; q < NW; ++q) {
+          if ((uint32_t)q == tw) top |= (uint32_t)(R[q] >> tsh);
+          if ((uint32_t)q == tw + 1u && tsh > 56u) top |= (uint32_t)(R[q] << (64u - tsh));
+        }
+        const uint64_t *row = T + (size_t)((top ^ dbyte) & 255u) * NW;
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      if ((uint32_t)k == hw) R[k] &= hmask;
-      if ((uint32_t)k > hw) R[k] = 0ull;
+        for (int q = NW - 1; q >= 0; --q) {
+          const uint64_t lo = q > 0 ? (R[q - 1] >> 56) : 0ull;
+          R[q] = ((R[q] << 8) | lo) ^ row[q];
+        }
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+          if ((uint32_t)q == hw) R[q] &= hmask;
+          if ((uint32_t)q > hw) R[q] = 0ull;
+        }
+      }
     }
+    __syncwarp();                                               // the tile is reloaded next
   }
-  // codeword words: parity | data shifted up by dg
-  uint64_t *out = cw_out + (size_t)cw * wpc;
-  const uint32_t sw = dg >> 6, sh = dg & 63u;
-  const uint32_t lastd = data_bits ? (data_bits - 1u) >> 6 : 0u;
-  for (uint32_t j = 0; j < wpc; ++j) {
-    uint64_t v = 0ull;
+
+  // shifted copy: output word j (32 bits) = data bits 32 j - dg .. 32 j - dg + 31
+  uint32_t *o32 = reinterpret_cast<uint32_t *>(cw_out);
+  const size_t ostride = (size_t)wpc * 2u;
+  const uint32_t sw = dg >> 5, sh = dg & 31u;
+  const uint32_t jpar = (dg - 1u) >> 5;                         // last output word that holds parity bits
+  auto shifted = [&](uint32_t c, uint32_t j) -> uint32_t {
+    if (j < sw) return 0u;
+    const uint32_t i = j - sw;
+    uint32_t v = dword(c, i) << sh;
+    if (sh && i >= 1u) v |= dword(c, i - 1u) >> (32u - sh);
+    return v;
+  };
+  for (uint32_t c = 0; c < 32u; ++c) {
+    if (cw0 + c >= batch) break;                                // (uniform)
+    for (uint32_t j = jpar + 1u + lane; j < 2u * wpc; j += 32u) o32[(size_t)(cw0 + c) * ostride + j] = shifted(cw0 + c, j);
+  }
+  if (cw < batch) {
+    for (uint32_t j = 0; j <= jpar && j < 2u * wpc; ++j) {
+      uint32_t par = 0u;
 #pragma unroll
-    for (int k = 0; k < NW; ++k)
-      if ((uint32_t)k == j) v = R[k];
-    if (data_bits && j >= sw) {
-      const uint32_t i = j - sw;
-      auto dword = [&](uint32_t w) -> uint64_t {
-        if (w > lastd) return 0ull;
-        uint64_t x = dsrc[w];
-        if (w == lastd && ((data_bits - 1u) & 63u) != 63u) x &= (2ull << ((data_bits - 1u) & 63u)) - 1ull;
-        return x;
-      };
-      v |= dword(i) << sh;
-      if (sh && i >= 1u) v |= dword(i - 1u) >> (64u - sh);
+      for (int q = 0; q < NW; ++q)
+        if ((uint32_t)q == (j >> 1)) par = (uint32_t)(R[q] >> (32u * (j & 1u)));
+      o32[(size_t)cw * ostride + j] = par | shifted(cw, j);
     }
-    out[j] = v;
   }
 }
+
 
 // Any generator degree >= 64 (the (8191, 200) and (65535, 1000) codes: deg g = 2444, 15360): one
 // WARP per codeword.  The remainder S (deg g bits) lives in shared memory as NS = deg g / 64 + 1

@@ -1084,7 +1084,7 @@ static int encode_launch(bchfft_code *c, const uint64_t *d_data, uint32_t dwords
                data_bits, c->gen_degree, (const uint64_t *)c->d_enc_table, d_cw, c->wpc, (uint32_t)batch);
     return BCHFFT_OK;
   }
-  const size_t smem = (size_t)256 * c->enc_nw * 8;
+  const size_t smem = (size_t)256 * c->enc_nw * 8 + (size_t)4 * 32 * 33 * 4;   // table + one staging tile per warp
   const dim3 grid((unsigned)((batch + 127) / 128)), block(128);
 #define ENC(NW)                                                                                        \
   case NW:                                                                                             \
