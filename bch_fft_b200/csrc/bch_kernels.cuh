@@ -1363,13 +1363,19 @@ k_locate_u(const uint32_t *__restrict__ F2, const uint32_t *__restrict__ counts,
 #pragma unroll 1
         for (uint32_t b = warp; b < ng; b += nwarps) job.radix4_wide(d, b);
       } else if (d >= 1u) {
+        // a warp's blocks alternate between the two ends of the block range (w, 2 nwarps - 1 - w, ..): with
+        // fewer than eight warps every warp gets cheap and expensive blocks of a zero-skipping first step
 #pragma unroll 1
-        for (uint32_t b = 0; b < 8u; ++b)
-          if ((b & (nwarps - 1u)) == warp) job.radix4(d, b, from_f, last);
+        for (uint32_t r = 0; r * nwarps < 8u; ++r) {
+          const uint32_t b = r * nwarps + ((r & 1u) ? nwarps - 1u - warp : warp);
+          if (b < 8u) job.radix4(d, b, from_f, last);      // (more than eight warps: the others idle)
+        }
       } else {
 #pragma unroll 1
-        for (uint32_t b = 0; b < 16u; ++b)
-          if ((b & (nwarps - 1u)) == warp) job.radix2_last(b, from_f);
+        for (uint32_t r = 0; r * nwarps < 16u; ++r) {
+          const uint32_t b = r * nwarps + ((r & 1u) ? nwarps - 1u - warp : warp);
+          if (b < 16u) job.radix2_last(b, from_f);
+        }
       }
       if (nsteps > 1u) __syncthreads();   // also keeps the next tile's first step off a buffer still being read
     }

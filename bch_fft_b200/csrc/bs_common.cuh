@@ -92,8 +92,16 @@ __host__ __device__ constexpr uint32_t field_poly(int m)
 }
 
 // plane words per element in HBM slabs: M rounded up to a multiple of 4 so that one element is
-// a whole number of 16-byte vectors
-__host__ __device__ constexpr int plane_stride(int m) { return (m + 3) & ~3; }
+// a whole number of 16-byte vectors; above GF(2^16) to a multiple of 8, so that an element is a whole
+// number of 32-byte sectors (an 80-byte element of GF(2^20) straddles 3.5 sectors on average) and the
+// Taylor-only passes can take 8-plane groups (k_ty_pass)
+#ifndef BCHFFT_PS_ALIGN8_ABOVE
+#define BCHFFT_PS_ALIGN8_ABOVE 16
+#endif
+__host__ __device__ constexpr int plane_stride(int m)
+{
+  return m > BCHFFT_PS_ALIGN8_ABOVE ? ((m + 7) & ~7) : ((m + 3) & ~3);
+}
 
 // three-input XOR: one LOP3
 __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c)

@@ -147,14 +147,19 @@ static int fft_run(bchfft_field *f, DeviceBuffer &ws, const uint32_t *d_polys, s
       const size_t src_words = (bw && !first_bw) ? bwd_words : fwd_words;
       const size_t dst_words = bw ? bwd_words : fwd_words;
       dim3 grid(1u << (pd.dom_bits - pd.t), (unsigned)cs);
-      bool ty_only = pd.nops > 0 && psrc == pdst && PS % 8 == 0 && pd.src_mask == 0xFFFFFFFFu;
+      // (plane strides that are only a multiple of 4 -- GF(2^17)..GF(2^20), GF(2^25) -- could run the same kernel
+      // on 4-plane groups; measured at m = 20: 1.17 ms per pass against 1.09 ms through k_gm_pass, the 16-byte
+      // accesses at an 80-byte stride use half of every sector.  BCHFFT_TY_PASS4=1 switches it on.)
+      bool ty_only = pd.nops > 0 && psrc == pdst && pd.src_mask == 0xFFFFFFFFu &&
+                     (PS % 8 == 0 || getenv("BCHFFT_TY_PASS4"));
       for (uint32_t k = 0; k < pd.nops && ty_only; k++) ty_only = pd.ops[k].type == OP_TY;
       if (ty_only) {
-        // XOR-only pass: eight planes per CTA (see k_ty_pass)
-        const size_t smem8 = ((size_t)4 * 8) << pd.t;
-        BCHFFT_ENSURE_SMEM(k_ty_pass<PS>, f->device, smem8);
-        grid.x *= PS / 8;
-        BCHFFT_RUN(k_ty_pass<PS>, grid, dim3(nt_ty), smem8, stream, pdst, dst_words, pd);
+        // XOR-only pass: eight (or four) planes per CTA (see k_ty_pass)
+        constexpr int MP = PS % 8 == 0 ? 8 : 4;
+        const size_t smem_ty = ((size_t)4 * MP) << pd.t;
+        BCHFFT_ENSURE_SMEM((k_ty_pass<PS, MP>), f->device, smem_ty);
+        grid.x *= PS / MP;
+        BCHFFT_RUN((k_ty_pass<PS, MP>), grid, dim3(nt_ty), smem_ty, stream, pdst, dst_words, pd);
         continue;
       }
       const size_t smem = ((size_t)4 * M) << pd.t;

@@ -802,29 +802,32 @@ k_gm_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t s
 
 // ---- Taylor-only pass on a group of planes --------------------------------------------------
 // A pass that contains only Taylor levels (XOR only, plane-wise) does not need whole elements:
-// each CTA takes MP = 8 of the PS plane words of every position of the tile (one 32-byte
-// sector), so its tile is half the size and three CTAs are resident per SM -- the load / sweep /
-// store phases of neighbouring CTAs overlap.  grid = (tiles * PS/8, slabs): the plane groups of
-// one tile are adjacent CTAs, so they run together and share the 64-byte DRAM bursts.
-template <int PSW>
+// each CTA takes MP = 8 (or 4, when the plane stride is not a multiple of 8: GF(2^17) .. GF(2^20),
+// GF(2^25)) of the PS plane words of every position of the tile, so its tile is a fraction of the
+// size and three or more CTAs are resident per SM -- the load / sweep / store phases of neighbouring
+// CTAs overlap.  grid = (tiles * PS/MP, slabs): the plane groups of one tile are adjacent CTAs, so they
+// run together and share the sectors / 64-byte DRAM bursts.
+template <int PSW, int MP>
 __global__ void __launch_bounds__(256, BCHFFT_MINB_TY)
 k_ty_pass(uint32_t *__restrict__ buf, size_t slab_words, PassDesc desc)
 {
-  constexpr int MP = 8, NG = PSW / 8;
+  static_assert(MP == 4 || MP == 8, "plane groups of one or two 16-byte vectors");
+  static_assert(PSW % MP == 0, "plane stride must split into whole groups");
+  constexpr int NG = PSW / MP, NV = MP / 4;
   BCHFFT_DYN_SMEM(uint32_t, S);
   const uint32_t T = 1u << desc.t;
   const TileGeom g = tile_geom(desc, blockIdx.x / NG);
   uint32_t *base = buf + (size_t)blockIdx.y * slab_words + (blockIdx.x % NG) * MP;
   constexpr int U = 4;
   for (uint32_t b0 = threadIdx.x; b0 < T; b0 += U * blockDim.x) {
-    uint4 q[U][2];
+    uint4 q[U][NV];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const uint32_t l = b0 + u * blockDim.x;
       if (l < T) {
         const uint4 *in = reinterpret_cast<const uint4 *>(base + (size_t)g.pos(l) * PSW);
-        q[u][0] = in[0];
-        q[u][1] = in[1];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) q[u][v] = in[v];
       }
     }
 #pragma unroll
@@ -832,14 +835,13 @@ k_ty_pass(uint32_t *__restrict__ buf, size_t slab_words, PassDesc desc)
       const uint32_t l = b0 + u * blockDim.x;
       if (l < T) {
         const uint32_t sl = swz(l);
-        S[0 * T + sl] = q[u][0].x;
-        S[1 * T + sl] = q[u][0].y;
-        S[2 * T + sl] = q[u][0].z;
-        S[3 * T + sl] = q[u][0].w;
-        S[4 * T + sl] = q[u][1].x;
-        S[5 * T + sl] = q[u][1].y;
-        S[6 * T + sl] = q[u][1].z;
-        S[7 * T + sl] = q[u][1].w;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          S[(4 * v + 0) * T + sl] = q[u][v].x;
+          S[(4 * v + 1) * T + sl] = q[u][v].y;
+          S[(4 * v + 2) * T + sl] = q[u][v].z;
+          S[(4 * v + 3) * T + sl] = q[u][v].w;
+        }
       }
     }
   }
@@ -855,8 +857,10 @@ k_ty_pass(uint32_t *__restrict__ buf, size_t slab_words, PassDesc desc)
   for (uint32_t l = threadIdx.x; l < T; l += blockDim.x) {
     const uint32_t sl = swz(l);
     uint4 *out = reinterpret_cast<uint4 *>(base + (size_t)g.pos(l) * PSW);
-    out[0] = make_uint4(S[0 * T + sl], S[1 * T + sl], S[2 * T + sl], S[3 * T + sl]);
-    out[1] = make_uint4(S[4 * T + sl], S[5 * T + sl], S[6 * T + sl], S[7 * T + sl]);
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      out[v] = make_uint4(S[(4 * v + 0) * T + sl], S[(4 * v + 1) * T + sl], S[(4 * v + 2) * T + sl],
+                          S[(4 * v + 3) * T + sl]);
   }
 }
 

@@ -81,11 +81,11 @@ def main():
     total = _lib.lib().bchfft_device_count()
     g = 1
     while g <= total:
-        for mode in ("patch", "words"):
+        for mode in ("positions", "words"):
             env = dict(os.environ, BCHFFT_DEVICES=",".join(str(i) for i in range(g)), BCHFFT_D2H_MODE=mode)
             env.pop("BCHFFT_DEVICE", None)
             subprocess.run([sys.executable, os.path.abspath(__file__), "--child", str(g), mode, str(per_dev),
-                            str(polys if mode == "patch" else 0)], env=env, check=False)
+                            str(polys if mode == "positions" else 0)], env=env, check=False)
         g *= 2
 
 
