@@ -92,11 +92,13 @@ __host__ __device__ constexpr uint32_t field_poly(int m)
 }
 
 // plane words per element in HBM slabs: M rounded up to a multiple of 4 so that one element is
-// a whole number of 16-byte vectors; above GF(2^16) to a multiple of 8, so that an element is a whole
-// number of 32-byte sectors (an 80-byte element of GF(2^20) straddles 3.5 sectors on average) and the
-// Taylor-only passes can take 8-plane groups (k_ty_pass)
+// a whole number of 16-byte vectors.  Build option: a multiple of 8 above GF(2^BCHFFT_PS_ALIGN8_ABOVE), so
+// that an element is a whole number of 32-byte sectors (an 80-byte element of GF(2^20) straddles 3.5 sectors
+// on average) and the Taylor-only passes take 8-plane groups (k_ty_pass).  Measured at m = 20 with the
+// option at 16: 22.3 ms per 256 polynomials against 19.2 ms -- 20 % more bytes per pass cost more than the
+// aligned sectors give back; off by default.
 #ifndef BCHFFT_PS_ALIGN8_ABOVE
-#define BCHFFT_PS_ALIGN8_ABOVE 16
+#define BCHFFT_PS_ALIGN8_ABOVE 99
 #endif
 __host__ __device__ constexpr int plane_stride(int m)
 {
