@@ -93,7 +93,10 @@ static int fft_run(bchfft_field *f, DeviceBuffer &ws, const uint32_t *d_polys, s
   const uint32_t ncoef = (num_terms >= n - 1u ? n - 1u : num_terms) + 1u;
   const int K = ceil_log2(ncoef);
   auto it = f->plans.find(K);
-  if (it == f->plans.end()) it = f->plans.emplace(K, gm_plan(M, K, f->t_max, f->twist_free)).first;
+  // (fields whose Cantor chain is a proper prefix: the twist-free depths run as a Cantor conversion;
+  // BCHFFT_NO_CANTOR_PREFIX=1 keeps their plain Taylor levels)
+  if (it == f->plans.end())
+    it = f->plans.emplace(K, gm_plan(M, K, f->t_max, f->twist_free, !getenv("BCHFFT_NO_CANTOR_PREFIX"))).first;
   const GmPlan &plan = it->second;
 
   // fully twist-free field, full-degree input, transform larger than a tile: plane-major path

@@ -794,7 +794,7 @@ k_gm_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t s
   BCHFFT_MARK(1);
   tile_load<M>(S, T, src + (size_t)blockIdx.y * src_slab_words, g, desc.src_mask);
   __syncthreads();
-  tile_run_ops<M, NoEpilogue, false, (BCHFFT_UNI_BF != 0 && M >= 13)>(S, T, desc.t, g, tab, desc);
+  tile_run_ops<M, NoEpilogue, true, (BCHFFT_UNI_BF != 0 && M >= 13)>(S, T, desc.t, g, tab, desc);
   BCHFFT_MARK(2);
   tile_store<M>(S, T, dst + (size_t)blockIdx.y * dst_slab_words, g);
   BCHFFT_MARK(3);

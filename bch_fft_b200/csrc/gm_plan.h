@@ -133,11 +133,80 @@ inline GmConstants gm_constants(int m, const uint32_t *exp, const uint32_t *log)
     }
     return false;
   };
-  for (size_t k = 0; k < chain.size(); k++) {
-    independent_insert(chain[k]);
-    basis[m - 1 - k] = chain[k];
+  const int cl = (int)chain.size();
+  bool periodic = false;
+  if (cl >= 2 && cl < m && m % cl == 0 && !(cl & (cl - 1))) {
+    // Periodic Cantor basis (m = cl * r, the chain lives in the subfield GF(2^cl)): after the cl
+    // twist-free depths of a group the remaining basis is the image of the unused elements under the
+    // GF(2^cl)-linear map x -> S(x / tau), S(y) = y^(2^cl) + y = s_cl(y).  Its image is a GF(2^cl)-space, so it
+    // contains tau' * (chain) for any nonzero tau' in it: choosing the next cl basis elements as preimages of
+    // tau' * chain makes the next group start with ONE twist (by tau') followed by cl - 1 twist-free depths.
+    // Twists drop from m - cl to m / cl - 1 (GF(2^20): 16 -> 4), and the Taylor levels of every group of
+    // cl depths merge into a conversion of base x^(2^cl) + x (gm_plan).
+    std::vector<uint32_t> taus;
+    auto inv = [&](uint32_t v) -> uint32_t { return exp[(order - log[v]) % order]; };
+    auto image = [&](uint32_t x) -> uint32_t {
+      for (uint32_t tau : taus) {
+        const uint32_t y = mul(x, inv(tau));
+        uint32_t z = y;
+        for (int i = 0; i < cl; i++) z = mul(z, z);
+        x = z ^ y;
+      }
+      return x;
+    };
+    periodic = true;
+    for (int j = 0; j * cl < m && periodic; j++) {
+      const int k = m - j * cl;
+      std::vector<uint32_t> img(m, 0u), pre(m, 0u);   // echelon over the images of the unit vectors
+      for (int b = 0; b < m; b++) {
+        uint32_t v = image(1u << b), pv = 1u << b;
+        for (int kk = m - 1; kk >= 0 && v; kk--) {
+          if (!((v >> kk) & 1u)) continue;
+          if (img[kk]) {
+            v ^= img[kk];
+            pv ^= pre[kk];
+          } else {
+            img[kk] = v;
+            pre[kk] = pv;
+            v = 0;
+          }
+        }
+      }
+      uint32_t tau = 1u;
+      if (j > 0) {
+        tau = 0u;
+        for (int kk = 0; kk < m && !tau; kk++) tau = img[kk];
+      }
+      if (!tau) {
+        periodic = false;
+        break;
+      }
+      for (int jj = 0; jj < cl; jj++) {
+        uint32_t v = mul(tau, chain[jj]), pv = 0u;
+        for (int kk = m - 1; kk >= 0 && v; kk--) {
+          if (!((v >> kk) & 1u)) continue;
+          if (!img[kk]) break;
+          v ^= img[kk];
+          pv ^= pre[kk];
+        }
+        if (v || !independent_insert(pv)) {
+          periodic = false;
+          break;
+        }
+        basis[k - 1 - jj] = pv;
+      }
+      taus.push_back(tau);
+    }
+    if (!periodic) {
+      std::fill(basis.begin(), basis.end(), 0u);
+      std::fill(ech.begin(), ech.end(), 0u);
+    }
   }
-  {
+  if (!periodic) {
+    for (size_t k = 0; k < chain.size(); k++) {
+      independent_insert(chain[k]);
+      basis[m - 1 - k] = chain[k];
+    }
     int slot = 0;
     for (int b = 0; b < m && slot < m - (int)chain.size(); b++)
       if (independent_insert(1u << b)) basis[slot++] = 1u << b;
@@ -283,17 +352,47 @@ inline void build_passes(std::vector<PassDesc> &out, const std::vector<PlanItem>
   } while (i < stream.size());
 }
 
+inline void cantor_conversion_ops(std::vector<PlanItem> &out, int b0, int w);
+
 // t_max: largest tile (log2 positions) that fits the CTA's shared memory for this M.
-inline GmPlan gm_plan(int m, int K, int t_max, uint32_t twist_free = 0u)
+// cantor_prefix: h consecutive depths d .. d + h - 1 without a twist between them (h a power of two; the
+// periodic Cantor basis of gm_constants gives runs of the chain length: 4 for GF(2^20), 8 for GF(2^24), 2
+// for GF(2^18)) have Taylor levels that are, as a formal identity on coefficient arrays, the expansion in
+// base x^(2^h) + x on the index bits d .. K-1 followed by the Cantor conversion of bits d .. d+h-1:
+// K - d - h levels OP_TX(k, h) and (h/2) log2(h) more instead of h (2 (K - d) - h - 1) / 2
+// (tools/gm_model.py: tx_level / cantor_conversion; checked against the Taylor levels for K up to 14 and every
+// offset d).  GF(2^20): 190 Taylor levels -> 60 generalised ones, 16 twists -> 4.
+inline GmPlan gm_plan(int m, int K, int t_max, uint32_t twist_free = 0u, bool cantor_prefix = false)
 {
   GmPlan plan;
   plan.m = m;
   plan.K = K;
   plan.t = t_max;
   std::vector<PlanItem> fwd, bwd;
-  for (int d = 0; d < K; d++) {
+  const int tcap = t_max < K ? t_max : K;
+  for (int d = 0; d < K;) {
     if (!((twist_free >> d) & 1u)) fwd.push_back({{OP_TW, (uint8_t)d, 0, 0}, 0u});
+    // depths d .. d + run - 1 have no twist between their Taylor levels
+    int run = 1;
+    while (d + run < K && ((twist_free >> (d + run)) & 1u)) run++;
+    int h = 0;
+    if (cantor_prefix) {
+      for (h = 1; 2 * h <= run; h *= 2) {}
+      while (h >= 2 && h + 1 > tcap) h /= 2;       // a level of base 2^h spans h + 1 position bits of one window
+      if (h < 2 || K - d < h) h = 0;
+    }
+    if (h) {
+      // Taylor levels of h consecutive depths = expansion in base x^(2^h) + x on the index bits d .. K-1
+      // followed by the Cantor conversion of the h bits d .. d + h - 1
+      for (int k = K - h - 1; k >= d; k--)
+        fwd.push_back({{OP_TX, (uint8_t)h, (uint8_t)k, 0}, ((2u << h) - 1u) << k});
+      cantor_conversion_ops(fwd, d, h);
+      d += h;
+      // the rest of the run continues without a twist: handled by the next iteration, which must not emit TW
+      continue;
+    }
     for (int lo = K - 2; lo >= d; lo--) fwd.push_back({{OP_TY, (uint8_t)d, (uint8_t)lo, 0}, 3u << lo});
+    d++;
   }
   for (int d = K - 1; d >= 0; d--) bwd.push_back({{OP_BF, (uint8_t)d, 0, 0}, 1u << d});
   if (K == m) {

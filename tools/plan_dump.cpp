@@ -33,16 +33,17 @@ int main(int argc, char **argv)
   // sanity: the basis spans the field and the position tables are inverse permutations
   bool perm_ok = true;
   for (uint32_t k = 0; k < n; k++) perm_ok &= c.elem_of_pos[c.pos_of_elem[k]] == k;
-  GmPlan plan = gm_plan(m, K, t, c.twist_free);
-  int ntw = 0, nty = 0, nbf = 0;
+  GmPlan plan = gm_plan(m, K, t, c.twist_free, !getenv("BCHFFT_NO_CANTOR_PREFIX"));
+  int ntw = 0, nty = 0, nbf = 0, ntx = 0;
   for (auto &p : plan.passes)
     for (uint32_t i = 0; i < p.nops; i++) {
       ntw += p.ops[i].type == OP_TW;
       nty += p.ops[i].type == OP_TY;
       nbf += p.ops[i].type == OP_BF;
+      ntx += p.ops[i].type == OP_TX;
     }
-  printf("m=%d K=%d t=%d twist_free_depths=%d perm_ok=%d passes=%zu tw_ops=%d ty_ops=%d bf_ops=%d\n", m, K, t,
-         chain, (int)perm_ok, plan.passes.size(), ntw, nty, nbf);
+  printf("m=%d K=%d t=%d twist_free_depths=%d perm_ok=%d passes=%zu tw_ops=%d ty_ops=%d bf_ops=%d tx_ops=%d\n", m, K, t,
+         chain, (int)perm_ok, plan.passes.size(), ntw, nty, nbf, ntx);
   for (auto &p : plan.passes) {
     uint32_t w = (((1u << p.n0) - 1u) << p.a0) | (p.n1 ? (((1u << p.n1) - 1u) << p.a1) : 0u);
     printf("  pass dom=%u t=%u window=0x%x ops=%u backward=%u\n", p.dom_bits, p.t, w, p.nops, p.backward);
