@@ -62,6 +62,11 @@
 #endif
 // radix-4 sweeps of the FFT pass kernels: the two butterflies that share a multiplier in one branch
 // sequence (bs_mad_uniform2; more registers live at once)
+// smallest base 2^h whose runs of generalised Taylor levels take the line sweep (up to six levels per
+// shared-memory round trip) instead of the two-level register programs
+#ifndef BCHFFT_TX_LINES_MIN_H
+#define BCHFFT_TX_LINES_MIN_H 5
+#endif
 #ifndef BCHFFT_R4_MAD2
 #define BCHFFT_R4_MAD2 0
 #endif

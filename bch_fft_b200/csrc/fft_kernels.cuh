@@ -565,7 +565,7 @@ __device__ __forceinline__ uint32_t tile_tx_sweep(uint32_t *S, uint32_t T, uint3
   auto is_c4 = [&](uint32_t k, uint32_t b) -> bool {
     return is_tx(k, b + 1u, 2u) && is_tx(k + 1u, b, 2u) && is_tx(k + 2u, b, 1u) && is_tx(k + 3u, b + 2u, 1u);
   };
-  if (op.d >= 5u) {
+  if (op.d >= BCHFFT_TX_LINES_MIN_H) {
     // run of levels of one large base: line sweep (at most six levels, super-block inside the tile)
     uint32_t n = 1u;
     while (n < 6u && op.lo >= n && is_tx(i + n, op.lo - n, op.d) &&

@@ -309,6 +309,20 @@ inline void set_window(PassDesc &p, uint32_t w)
   p.t = p.n0 + p.n1;
 }
 
+// Position bits every window of the generic schedule must contain.  Default (0xFFFFFFFF = automatic): bit 0
+// when an element ((m + 3) & ~3 plane words) is not a whole number of 32-byte sectors -- GF(2^17)..GF(2^20):
+// 80 bytes, GF(2^25): 112 -- so that a tile row moves pairs of elements, i.e. whole sectors.  Measured at
+// m = 20, ms per 256 polynomials: no required bit 11.5, bit 0 9.2, bits 0 and 1 (one pass more) 10.5.
+#ifndef BCHFFT_GM_REQUIRED_BITS
+#define BCHFFT_GM_REQUIRED_BITS 0xFFFFFFFFu
+#endif
+inline uint32_t gm_required_bits(int m)
+{
+  const uint32_t r = BCHFFT_GM_REQUIRED_BITS;
+  if (r != 0xFFFFFFFFu) return r;
+  return ((((m + 3) & ~3) * 4) % 32) ? 1u : 0u;
+}
+
 struct GmPlan {
   int m, K, t;
   std::vector<PassDesc> passes;  // forward passes first, then backward passes
@@ -332,6 +346,11 @@ inline void build_passes(std::vector<PassDesc> &out, const std::vector<PlanItem>
     PassDesc p;
     memset(&p, 0, sizeof p);
     uint32_t w = required;
+    // (an op that does not fit next to the required bits gets a window without them)
+    if (i < stream.size() && required) {
+      const uint32_t cand = w | stream[i].bits;
+      if (__builtin_popcount(cand) > t || bit_runs(cand) > 2) w = 0u;
+    }
     while (i < stream.size() && p.nops < (uint32_t)kMaxOps) {
       const uint32_t cand = w | stream[i].bits;
       if (__builtin_popcount(cand) > t || bit_runs(cand) > 2) break;
@@ -353,6 +372,23 @@ inline void build_passes(std::vector<PassDesc> &out, const std::vector<PlanItem>
 }
 
 inline void cantor_conversion_ops(std::vector<PlanItem> &out, int b0, int w);
+
+// With `required` bits (see gm_required_bits) a pass is about a fifth cheaper (whole sectors per tile row)
+// but the windows have fewer free bits: take them only when that costs at most one pass in eight.
+inline void build_passes_sector_aware(std::vector<PassDesc> &out, const std::vector<PlanItem> &stream, int dom,
+                                      int t_max, bool backward, uint32_t src_mask_first, uint32_t required)
+{
+  std::vector<PassDesc> plain, aligned;
+  build_passes(plain, stream, dom, t_max, backward, src_mask_first, 0u);
+  if (required && dom > t_max && t_max >= 8) {
+    build_passes(aligned, stream, dom, t_max, backward, src_mask_first, required);
+    if (aligned.size() * 8 <= plain.size() * 9) {
+      out.insert(out.end(), aligned.begin(), aligned.end());
+      return;
+    }
+  }
+  out.insert(out.end(), plain.begin(), plain.end());
+}
 
 // t_max: largest tile (log2 positions) that fits the CTA's shared memory for this M.
 // cantor_prefix: h consecutive depths d .. d + h - 1 without a twist between them (h a power of two; the
@@ -402,12 +438,13 @@ inline GmPlan gm_plan(int m, int K, int t_max, uint32_t twist_free = 0u, bool ca
     std::vector<PlanItem> all = fwd;
     all.insert(all.end(), bwd.begin(), bwd.end());
     plan.first_backward = 0;
-    build_passes(plan.passes, all, m, t_max, true, 0xFFFFFFFFu);
+    build_passes_sector_aware(plan.passes, all, m, t_max, true, 0xFFFFFFFFu, gm_required_bits(m));
     return plan;
   }
   if (!fwd.empty()) build_passes(plan.passes, fwd, K, t_max, false, 0xFFFFFFFFu);   // K = 0: constant polynomial
   plan.first_backward = (int)plan.passes.size();
-  build_passes(plan.passes, bwd, m, t_max, true, K < m ? ((1u << K) - 1u) : 0xFFFFFFFFu);
+  build_passes_sector_aware(plan.passes, bwd, m, t_max, true, K < m ? ((1u << K) - 1u) : 0xFFFFFFFFu,
+                            gm_required_bits(m));
   return plan;
 }
 

@@ -107,7 +107,7 @@ def test_gf2_16_is_nine_passes(plan_dump):
     # generic tile schedule with the grouped Cantor conversion: five passes; GF(2^20): 9 instead of 17
     head, passes = run(plan_dump, 16, 16, 11)
     assert head["passes"] == 5 and head["tw_ops"] == 0
-    assert run(plan_dump, 20, 20, 11, prefix=False)[0]["passes"] == 17
+    assert run(plan_dump, 20, 20, 11, prefix=False)[0]["passes"] == 17      # plain Taylor levels, no required bit
     head20, _ = run(plan_dump, 20, 20, 11)
     assert head20["passes"] == 9 and head20["tw_ops"] == 4 and head20["tx_ops"] == 60 and head20["ty_ops"] == 0
 

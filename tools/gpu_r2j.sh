@@ -19,3 +19,7 @@ CMD2="python bench.py --small --steps 2 --warmup 1 --batch 32768 --fft-batch 0 -
 timeout 900 ncu --set full --clock-control none -k regex:"^k_locate$|^k_locate_u$|^k_elp_fwd$|^k_bm$|^k_gm_pass$|^k_ty_pass$|k_mfft16|^k_syndrome_p$" -c 60 -o /tmp/ncu_side_$tag $CMD2 > gpurun_out/${tag}_ncu_full_side.log 2>&1; echo "ncu side rc=$?"
 ncu -i /tmp/ncu_side_$tag.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_raw_side.csv 2>/dev/null
 ls -la gpurun_out | grep $tag
+# GF(2^20) generic schedule: its pass kernel on its own (the side capture above stops before it)
+CMD3="python bench.py --small --steps 2 --warmup 1 --batch 32768 --fft-batch 0 --no-cpu-baseline --no-e2e --only fft20"
+timeout 900 ncu --set full --clock-control none -k regex:"^k_gm_pass$" -c 12 -o /tmp/ncu_fft20_$tag $CMD3 > gpurun_out/${tag}_ncu_full_fft20.log 2>&1; echo "ncu fft20 rc=$?"
+ncu -i /tmp/ncu_fft20_$tag.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_raw_fft20.csv 2>/dev/null
