@@ -117,7 +117,9 @@ def _words_for(pc, n, t, B, rng):
 
 @pytest.mark.parametrize("n,t", [(15, 2), (63, 5), (255, 8), (255, 20), (1023, 10), (300, 3), (5000, 12),
                                  (8191, 8), (8191, 16), (8191, 64), (8191, 200), (65535, 16),
-                                 (65535, 100), (65535, 1000)])
+                                 (65535, 100), (65535, 1000),
+                                 # fields with a periodic Cantor basis (m = 12: groups of 4 depths, m = 14: of 2)
+                                 (4095, 12), (4095, 40), (16383, 10)])
 def test_bch_stages_and_decode_vs_oracle(gpu_libs, port, n, t):
     cabi, _ = gpu_libs
     pc = port.code(n, t)
