@@ -1038,7 +1038,7 @@ __device__ __forceinline__ size_t f2_index(uint32_t group, uint32_t kmax, uint32
 // grid = (ceil(slabs / 8), kmax), bucket K = blockIdx.y + 1 (K <= 5 here), a CTA takes 256
 // coefficient columns = 2^(8-K) slabs; fwd_descs[K] = forward pass of bucket K.
 template <int M>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, BCHFFT_MINB_ELPU)
 k_elp_fwd_u(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin, uint32_t d,
             const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists, uint32_t batch,
             uint32_t kmax, FftTables tab, const PassDesc *__restrict__ fwd_descs, uint32_t *__restrict__ F2)

@@ -76,6 +76,11 @@
 #ifndef BCHFFT_MINB_LOCU
 #define BCHFFT_MINB_LOCU 3
 #endif
+// k_elp_fwd_u waits on chains of dependent global loads (list -> codeword -> degree / coefficients): resident
+// CTAs per SM the kernel is compiled for (1: 254 registers per thread, 8 warps per SM)
+#ifndef BCHFFT_MINB_ELPU
+#define BCHFFT_MINB_ELPU 1
+#endif
 #ifndef BCHFFT_NT_SYN
 #define BCHFFT_NT_SYN 256
 #endif
