@@ -883,7 +883,7 @@ __global__ void k_bucket_scatter(const int32_t *__restrict__ flag, const uint32_
 // beyond the bucket's population exit); dynamic smem = M * 2^(K+sb) words.
 // Fout: [virtual slab][2^Kmax][PS] with virtual slab = vbase(bucket) + slab in bucket.
 template <int M>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, BCHFFT_MINB_ELPU)
 k_elp_fwd(const uint32_t *__restrict__ elp, const uint32_t *__restrict__ Lin, uint32_t d,
           const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists, uint32_t batch,
           uint32_t sb, uint32_t kmax, FftTables tab, PassDesc fwd, uint32_t *__restrict__ Fout)

@@ -76,10 +76,11 @@
 #ifndef BCHFFT_MINB_LOCU
 #define BCHFFT_MINB_LOCU 3
 #endif
-// k_elp_fwd_u waits on chains of dependent global loads (list -> codeword -> degree / coefficients): resident
-// CTAs per SM the kernel is compiled for (1: 254 registers per thread, 8 warps per SM)
+// k_elp_fwd_u / k_elp_fwd wait on chains of dependent global loads (list -> codeword -> degree / coefficients):
+// resident CTAs per SM the kernels are compiled for.  Measured, k_elp_fwd_u per 10^6 words: 1 CTA (254 registers
+// per thread, 8 warps per SM) 0.32 ms, 2: 0.18, 3: 0.15, 4 (64 registers): 0.13 ms.
 #ifndef BCHFFT_MINB_ELPU
-#define BCHFFT_MINB_ELPU 1
+#define BCHFFT_MINB_ELPU 4
 #endif
 #ifndef BCHFFT_NT_SYN
 #define BCHFFT_NT_SYN 256
