@@ -1583,9 +1583,24 @@ __global__ void k_correct(uint64_t *__restrict__ words, uint32_t words_per_cw, u
       // result mode of bchfft_bch_decode_host); only the verdict is needed here
       if (found == L && flip_on_device) {
         uint64_t *w = words + (size_t)cw * words_per_cw;
-        for (uint32_t i = 0; i < found; ++i) {
-          const uint32_t p = positions[(size_t)cw * pos_stride + i];
-          if ((p >> 6) < words_per_cw) w[p >> 6] ^= 1ull << (p & 63u);
+        if (!patch_dst) {
+          // XOR reductions that return nothing: the thread issues all of its flips without waiting for any
+          // (a read-modify-write per flip made this kernel a chain of found dependent DRAM round trips)
+          const uint32_t *pp = positions + (size_t)cw * pos_stride;
+          for (uint32_t i = 0; i < found; i += 4u) {
+            uint32_t p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = i + (uint32_t)u < found ? pp[i + (uint32_t)u] : 0xFFFFFFFFu;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if ((p[u] >> 6) < words_per_cw)
+                atomicXor(reinterpret_cast<unsigned long long *>(w + (p[u] >> 6)), 1ull << (p[u] & 63u));
+          }
+        } else {
+          for (uint32_t i = 0; i < found; ++i) {
+            const uint32_t p = positions[(size_t)cw * pos_stride + i];
+            if ((p >> 6) < words_per_cw) w[p >> 6] ^= 1ull << (p & 63u);
+          }
         }
         if (patch_dst) {
           // final values (two flips may share a word: both writes then carry the same value)
