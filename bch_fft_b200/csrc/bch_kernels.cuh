@@ -6,14 +6,15 @@
 //   k_syndrome     same result, general path: one masked LFSR per class
 //   k_syn_finish   un-bitslice, S_2j = S_j^2, zero test (stage-level API; the decode pipeline lets
 //                  k_bm do it)
-//   k_bm           Berlekamp-Massey, one thread per codeword (bch.c:328-404), shared-memory resident
-//                  for small fields
-//   k_bucket / k_elp_fwd[_u]   sort by locator degree, forward phase of the truncated FFT
+//   k_bm           Berlekamp-Massey, one thread or a lane group per codeword (bch.c:328-404), shared-memory
+//                  resident for small fields; k_bm_wide: one CTA per codeword
+//   k_bucket_count / k_bucket_scatter   counting sort by locator degree; degrees 1 and 2 solved in closed form
+//   k_elp_fwd[_u]  forward phase of the truncated FFT on the locator coefficients
 //   k_locate_u     error-locator evaluation at every field point, K <= 7 levels, warp lanes = slabs,
 //                  warp-uniform multipliers (bch.c:406-490)
 //   k_locate       same result, general path (tile engine, lanes = positions)
 //   k_correct      ok / corrected bookkeeping and the bit flips (bch.c:531-561)
-//   k_encode       systematic encoder (bch.c:492-506)
+//   k_encode / k_encode_wide   systematic encoder (bch.c:492-506)
 #pragma once
 #include <type_traits>
 #include "bs_common.cuh"
@@ -750,7 +751,7 @@ __global__ void k_bm_wide(const uint32_t *__restrict__ syn, const int32_t *__res
 // truncated transform is K = ceil(log2(L+1)) butterfly levels over all points, so codewords are
 // first sorted into buckets by K and packed into slabs per bucket: a slab of degree-3 locators
 // runs 2 levels, not the 5 a degree-16 locator needs.
-//   k_bucket    counting sort of the codewords that need a root search by K
+//   k_bucket_*  counting sort of the codewords that need a root search by locator degree (buckets K)
 //   k_elp_fwd   per bucket: bitslice the locator coefficients of 2^sb slabs per CTA and run the
 //               forward phase (twists + Taylor expansions) on the 2^K coefficients
 //   k_locate    one launch over the slabs of all buckets: per tile of 2^t positions broadcast

@@ -307,7 +307,7 @@ extern "C" int bchfft_field_create(int device, uint32_t m, const uint32_t *exp, 
     errloc[p] = k ? (n - 1u) - log[k] : 0xFFFFFFFFu;
   }
   f->twist_free = c.twist_free;
-  // y^2 + y = u, solved bit by bit (k_bucket's closed-form roots of degree-2 locators): trace of every
+  // y^2 + y = u, solved bit by bit (k_bucket_count's closed-form roots of degree-2 locators): trace of every
   // x^k, one trace-one element tau, h_k with h_k^2 + h_k = x^k + Tr(x^k) tau
   std::vector<uint32_t> qsolve(1u + m, 0u);
   {

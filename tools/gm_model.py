@@ -178,3 +178,40 @@ if __name__ == "__main__":
             got = natural(F, gm_fft(F, coef, K, c))
             assert (got == nat).all(), (m, K)
         print("m", m, "ok")
+
+
+def taylor_group_xor(a, K, d0, depths):
+    """Taylor levels of the depths d0 .. d0 + depths - 1 (no twist between them) on 2^K coefficients"""
+    a = a.copy()
+    pos = np.arange(1 << K)
+    for d in range(d0, d0 + depths):
+        for lo in range(K - 2, d - 1, -1):
+            q = 1 << lo
+            sel = (((pos >> (lo + 1)) & 1) == 1) & (((pos >> lo) & 1) == 0)
+            a[pos[sel]] ^= a[pos[sel] + q]
+            sel = (((pos >> (lo + 1)) & 1) == 0) & (((pos >> lo) & 1) == 1)
+            a[pos[sel]] ^= a[pos[sel] + q]
+    return a
+
+
+def grouped_conversion(a, K, d0, h):
+    """what gm_plan.h emits for such a group (h a power of two): K - d0 - h levels of base x^(2^h) + x on the
+    index bits d0 .. K-1, then the Cantor conversion of bits d0 .. d0 + h - 1"""
+    a = a.copy()
+    for k in range(K - h - 1, d0 - 1, -1):
+        tx_level(a, K, k, h)
+    cantor_conversion(a, K, d0, h)
+    return a
+
+
+def check_grouped_conversion():
+    rng = np.random.default_rng(5)
+    for K, d0, h in ((6, 0, 2), (9, 0, 4), (13, 0, 4), (14, 0, 8), (12, 4, 4), (12, 8, 4), (13, 4, 4),
+                     (14, 2, 2), (14, 4, 2), (10, 6, 4), (8, 4, 4)):
+        a = rng.integers(0, 1 << 30, 1 << K)
+        assert (taylor_group_xor(a, K, d0, h) == grouped_conversion(a, K, d0, h)).all(), (K, d0, h)
+    print("grouped Cantor conversion == Taylor levels of the group (every offset)")
+
+
+if __name__ == "__main__":
+    check_grouped_conversion()

@@ -1,0 +1,10 @@
+#!/bin/bash
+# round 2: launch list + --set full capture of the decode kernels of the final code (after k_elp_fwd_u / k_correct changed)
+tag=${1:-r2x}
+mkdir -p gpurun_out
+CMD="python bench.py --steps 2 --warmup 1 --batch 131072 --fft-batch 1024 --no-cpu-baseline --no-e2e --only fft"
+timeout 600 $CMD > gpurun_out/${tag}_plain.json 2> gpurun_out/${tag}_plain.err; echo "plain rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_ncu.csv $CMD > gpurun_out/${tag}_ncu_launch.log 2>&1; echo "launch list rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_syndrome_p|k_bm|k_bucket|k_elp_fwd_u|k_locate_u|k_correct" -c 7 -o /tmp/ncu_dec_$tag $CMD > gpurun_out/${tag}_ncu_full_dec.log 2>&1; echo "ncu decode rc=$?"
+ncu -i /tmp/ncu_dec_$tag.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_raw_decode.csv 2>/dev/null
+ls -la gpurun_out | grep $tag
