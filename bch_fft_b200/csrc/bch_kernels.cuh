@@ -1021,11 +1021,14 @@ k_locate(const uint32_t *__restrict__ F, const uint32_t *__restrict__ counts,
 // last step feeds the zero test).
 constexpr int kLocUMaxK = 7;
 // root queue entries per CTA (kernel parameter qcap; BCHFFT_LOCU_QUEUE overrides it so that tests can
-// force the drain and overflow paths; the emulator build defaults to a tiny queue for the same reason)
+// force the drain and overflow paths; the emulator build defaults to a tiny queue for the same reason).
+// Shared memory the queue does not take is L1 for the forward-value loads of the first step, frequent drains
+// cost barriers: measured per 10^6 words at (8191, 16), 4096 entries 4.46 ms, 2048: 4.30, 1024: 4.31, 512: 4.34,
+// 256: 4.46, 128: 4.72 ms.
 #ifdef BCHFFT_EMU
 constexpr uint32_t kLocUQueue = 24;
 #else
-constexpr uint32_t kLocUQueue = 4096;
+constexpr uint32_t kLocUQueue = 2048;
 #endif
 
 // F2 index of (group, coefficient i, plane b, lane)
