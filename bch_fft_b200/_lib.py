@@ -43,6 +43,7 @@ _SIGNATURES = {
     "bchfft_dev_free": (C.c_int, [C.c_int, _vp]),
     "bchfft_pinned_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
     "bchfft_pinned_free": (C.c_int, [_vp]),
+    "bchfft_set_concurrent_hosts": (None, [C.c_int]),
     "bchfft_dev_upload": (C.c_int, [C.c_int, _vp, _vp, _sz]),
     "bchfft_dev_download": (C.c_int, [C.c_int, _vp, _vp, _sz]),
     "bchfft_profile_begin": (C.c_int, []),

@@ -967,7 +967,10 @@ static size_t flip_threads()
   // one GPU with 54 M: 2 threads 38.7, 4 threads 49.5 M codewords/s end to end; two ranks with 2 threads
   // each 54.8 M against 79.3 M with 4 each (profiles/r2d_e2e_result_modes_1gpu.jsonl, r2m_*).
   const char *lws = getenv("LOCAL_WORLD_SIZE");
-  const size_t ranks = lws && atoi(lws) >= 1 ? (size_t)atoi(lws) : 1;
+  size_t ranks = lws && atoi(lws) >= 1 ? (size_t)atoi(lws) : 1;
+  // ... or with the other devices one process drives at once (bchfft_set_concurrent_hosts)
+  const size_t peers = (size_t)g_concurrent_hosts.load();
+  if (peers > ranks) ranks = peers;
   size_t n = std::thread::hardware_concurrency() / (2 * ranks);
   return n < 2 ? 2 : (n > 8 ? 8 : n);
 }

@@ -16,6 +16,7 @@ namespace bchfft {
 
 void set_error(const char *fmt, ...);
 extern std::atomic<uint64_t> g_launches;
+extern std::atomic<int> g_concurrent_hosts;   // *_host calls a host driver runs at once in this process
 
 #define BCHFFT_CUDA_TRY(expr)                                                              \
   do {                                                                                     \

@@ -10,6 +10,7 @@ namespace bchfft {
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_concurrent_hosts{1};
 
 void set_error(const char *fmt, ...)
 {
@@ -216,6 +217,8 @@ extern "C" int bchfft_pinned_alloc(size_t bytes, void **out)
   BCHFFT_CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1));
   return BCHFFT_OK;
 }
+
+extern "C" void bchfft_set_concurrent_hosts(int n) { bchfft::g_concurrent_hosts.store(n < 1 ? 1 : n); }
 
 extern "C" int bchfft_pinned_free(void *p)
 {

@@ -205,6 +205,7 @@ int bchfft_host_run_sharded(size_t count, size_t min_per_device, bchfft_shard_fn
   if (min_per_device < 1) min_per_device = 1;
   if ((size_t) g > count / min_per_device) g = (int) (count / min_per_device);
   if (g <= 1) return fn(0, 0, count, arg);
+  bchfft_set_concurrent_hosts(g);   /* host helper threads of the g concurrent device calls share this machine */
   /* ranges in multiples of 32 items (one slab), so that no device sees a ragged slab in the middle */
   size_t per = (count + (size_t) g - 1) / (size_t) g;
   per = (per + 31) / 32 * 32;
@@ -239,6 +240,7 @@ int bchfft_host_run_sharded(size_t count, size_t min_per_device, bchfft_shard_fn
     if (started[k]) pthread_join(th[k], NULL);
     if (!status && jobs[k].status) { status = jobs[k].status; err = jobs[k].err; }
   }
+  bchfft_set_concurrent_hosts(1);
   if (status && err != jobs[0].err) bchfft_set_last_error(err);
   return status;
 }

@@ -147,6 +147,11 @@ int bchfft_dev_download(int device, void *h_dst, const void *d_src, size_t bytes
 int bchfft_pinned_alloc(size_t bytes, void **out);
 int bchfft_pinned_free(void *p);
 
+/* Hint from a host driver that runs `n` *_host calls at once, one per device, from one process (the drop-in
+ * library's sharded batch calls): the helper threads a call starts on the host (the bit flips of the positions
+ * result mode) are then sized for a host shared between n such calls.  n < 1 counts as 1. */
+void bchfft_set_concurrent_hosts(int n);
+
 /* launch counter: number of kernels this library has launched since the last reset
  * (bench.py reports it as gpu_launches) */
 uint64_t bchfft_launch_count(void);
