@@ -961,17 +961,19 @@ static size_t flip_threads()
 {
   const char *env = getenv("BCHFFT_FLIP_THREADS");
   if (env && atoi(env) >= 1 && atoi(env) <= 64) return (size_t)atoi(env);
-  // Half of the host's hardware threads, shared with the other ranks of a one-process-per-GPU job (torchrun
-  // exports LOCAL_WORLD_SIZE), between 2 and 8.  Measured on 16 vCPUs: one flipping thread keeps up with
-  // about 15 M codewords/s (the flips are cache misses into the caller's array), the host-to-device copy of
-  // one GPU with 54 M: 2 threads 38.7, 4 threads 49.5 M codewords/s end to end; two ranks with 2 threads
-  // each 54.8 M against 79.3 M with 4 each (profiles/r2d_e2e_result_modes_1gpu.jsonl, r2m_*).
+  // The host's hardware threads divided between the ranks of a one-process-per-GPU job (torchrun exports
+  // LOCAL_WORLD_SIZE) or the devices one process drives at once (bchfft_set_concurrent_hosts), between 2 and 8
+  // per call.  Measured: one flipping thread keeps up with about 15 M codewords/s (the flips are cache misses
+  // into the caller's array), the host-to-device copy of one GPU with 54 M.  16 vCPUs, one GPU: 2 threads 38.7,
+  // 4 threads 49.5 M codewords/s end to end; 24 vCPUs, two ranks: 2 threads each 54.8 M, 4 each 79.3 M; 32
+  // vCPUs, eight devices in one process: 1 thread each 88, 2 each 90, 4 each 99, 8 each 98 M codewords/s
+  // (profiles/r2d_e2e_result_modes_1gpu.jsonl, r2m_*, r2zz_*).
   const char *lws = getenv("LOCAL_WORLD_SIZE");
   size_t ranks = lws && atoi(lws) >= 1 ? (size_t)atoi(lws) : 1;
   // ... or with the other devices one process drives at once (bchfft_set_concurrent_hosts)
   const size_t peers = (size_t)g_concurrent_hosts.load();
   if (peers > ranks) ranks = peers;
-  size_t n = std::thread::hardware_concurrency() / (2 * ranks);
+  size_t n = std::thread::hardware_concurrency() / ranks;
   return n < 2 ? 2 : (n > 8 ? 8 : n);
 }
 
