@@ -406,7 +406,10 @@ static int launch_locate(bchfft_code *c, bchfft_code::WorkSet &w, size_t cnt, co
     }
     // enough CTAs per group to fill the machine and to even out the buckets' different costs
     const unsigned ntiles = (1u << M) >> 5;
-    unsigned gx = (2400u + ngroups - 1u) / ngroups;
+    // (measured at 10^6 words of (8191, 16): 2400 CTAs 4.30 ms, 9000..40000 CTAs 4.00..4.06 ms)
+    const char *cenv = getenv("BCHFFT_LOCU_CTAS");       // target number of CTAs of the launch
+    const unsigned want_ctas = cenv && atoi(cenv) >= 1 ? (unsigned)atoi(cenv) : 16000u;
+    unsigned gx = (want_ctas + ngroups - 1u) / ngroups;
     if (gx > ntiles) gx = ntiles;
     if (gx < 1u) gx = 1u;
     uint32_t qcap = kLocUQueue;

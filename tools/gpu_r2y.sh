@@ -1,7 +1,7 @@
 #!/bin/bash
-# k_locate_u root-queue capacity (shared memory not used by the queue is L1 for the forward-value loads)
+# k_locate_u: number of CTAs per launch (tile ranges per group)
 mkdir -p gpurun_out
-for v in "BCHFFT_LOCU_QUEUE=4096" "BCHFFT_LOCU_QUEUE=2048" "BCHFFT_LOCU_QUEUE=1024" "BCHFFT_LOCU_QUEUE=512" "BCHFFT_LOCU_QUEUE=256" "BCHFFT_LOCU_QUEUE=128"; do
+for v in "BCHFFT_LOCU_CTAS=9000" "BCHFFT_LOCU_CTAS=16000" "BCHFFT_LOCU_CTAS=24000" "BCHFFT_LOCU_CTAS=40000"; do
   env $v timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --fft-batch 0 --only t64 > gpurun_out/r2y_var.json 2> gpurun_out/r2y_var.err || { echo "bench failed for $v"; tail -3 gpurun_out/r2y_var.err; continue; }
   python - "$v" gpurun_out/r2y_var.json <<'PY'
 import json, sys
